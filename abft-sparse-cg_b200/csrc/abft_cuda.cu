@@ -1,0 +1,781 @@
+// abft_cuda.cu -- the C ABI of include/abft_cuda.h: host orchestration of the
+// sm_100a kernels in spmv.cuh / vecops.cuh / encode.cuh.  No CPU fallback: if no
+// CUDA device is usable every entry point fails and says so.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ecc.cuh"
+#include "encode.cuh"
+#include "spmv.cuh"
+#include "vecops.cuh"
+
+using namespace abft;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *what, const char *file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s (%s:%d)", what, file, line);
+  g_last_error = buf;
+  return code ? code : -1;
+}
+
+#define CK(call)                                                                    \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) return fail((int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKP(call)                                                    \
+  do {                                                               \
+    cudaError_t e_ = (call);                                         \
+    if (e_ != cudaSuccess) {                                         \
+      fail((int)e_, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+      return nullptr;                                                \
+    }                                                                \
+  } while (0)
+#define REQUIRE(cond, msg)                                  \
+  do {                                                      \
+    if (!(cond)) return fail(-1, msg, __FILE__, __LINE__);  \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------
+enum { SLOT_SPMV_DOT = ABFT_SLOT_SPMV_DOT, SLOT_DOT = 1, SLOT_XR = 2, SLOT_RR0 = 3, SLOT_RR1 = 4 };
+
+struct abft_vector {
+  double *d = nullptr;
+  int N = 0;
+  bool owns = false;
+  double *h_stage = nullptr;  // pinned, allocated on first map
+};
+
+struct abft_matrix {
+  MatView view{};
+  uint32_t *d_rowptr = nullptr;
+  Tile *d_tiles = nullptr;
+  int n_tiles = 0;
+  int64_t nnz_offset = 0;
+};
+
+struct abft_ctx {
+  int mode = 0;
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  DevLog *d_log = nullptr;
+  unsigned int *h_flag = nullptr;   // mapped pinned
+  double *d_scalars = nullptr;      // kNumSlots
+  double *h_scalars = nullptr;      // mapped pinned mirror
+  double *d_partials = nullptr;     // kMaxPartials
+  unsigned int *d_counter = nullptr;
+  int *d_loop = nullptr;            // [0],[1] = active flags (ring of 2), [2] = iterations done
+  int *h_loop = nullptr;            // mapped pinned mirror: [0] = iterations, [1] = next-active
+  uint64_t launches = 0;
+  // fused dot(vec, result) left behind by the last spmv
+  const double *dot_a = nullptr, *dot_b = nullptr;
+  int dot_n = 0;
+  uint64_t dot_epoch = 0;
+  uint64_t epoch = 1;  // bumped by every call that writes vector data
+};
+
+static const char *kModeNames[ABFT_MODE_COUNT] = {"none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"};
+
+static bool g_tables_ready[64] = {false};
+
+static int ensure_tables(int device) {
+  if (device >= 0 && device < 64 && g_tables_ready[device]) return 0;
+  std::vector<uint32_t> tab(1024);
+  for (int s = 0; s < 4; s++)
+    for (uint32_t i = 0; i < 256; i++) tab[s * 256 + i] = crc32c_table_entry(i, s);
+  CK(cudaMemcpyToSymbol(g_crc_tab, tab.data(), sizeof(uint32_t) * 1024));
+  if (device >= 0 && device < 64) g_tables_ready[device] = true;
+  return 0;
+}
+
+static ReduceOut make_reduce(abft_ctx *c, int slot) {
+  ReduceOut r{};
+  r.partials = c->d_partials;
+  r.counter = c->d_counter;
+  r.dev = c->d_scalars + slot;
+  r.host = c->h_scalars + slot;
+  r.active = nullptr;
+  r.iters = nullptr;
+  r.threshold = 0.0;
+  r.max_itrs = 0;
+  r.bump_iters = 0;
+  return r;
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int vec_grid(const abft_ctx *c, int N) {
+  long long want = ((long long)(N / 2 + 1) + kBlock - 1) / kBlock;
+  long long cap = (long long)c->num_sms * 8;
+  return (int)std::max(1LL, std::min(want, cap));
+}
+
+// ---------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int abft_cuda_abi_version(void) { return ABFT_CUDA_ABI_VERSION; }
+const char *abft_cuda_last_error(void) { return g_last_error.c_str(); }
+
+const char *abft_cuda_mode_name(int mode) {
+  return (mode >= 0 && mode < ABFT_MODE_COUNT) ? kModeNames[mode] : nullptr;
+}
+
+int abft_cuda_mode_from_name(const char *s) {
+  if (!s) return -1;
+  for (int i = 0; i < ABFT_MODE_COUNT; i++)
+    if (!strcmp(s, kModeNames[i])) return i;
+  return -1;
+}
+
+int abft_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int abft_cuda_event_is_fatal(int kind) {
+  return !(kind == ABFT_EV_CORRECTED_BIT || kind == ABFT_EV_CORRECTED_PARITY);
+}
+
+int abft_cuda_format_event(const abft_event *e, char *buf, int buflen) {
+  switch (e->kind) {
+    case ABFT_EV_SED_DETECTED: return snprintf(buf, buflen, "[ECC] error detected at index %d", (int)e->index);
+    case ABFT_EV_CORRECTED_BIT: return snprintf(buf, buflen, "[ECC] corrected bit %u at index %d", e->bit, (int)e->index);
+    case ABFT_EV_CORRECTED_PARITY: return snprintf(buf, buflen, "[ECC] corrected overall parity bit at index %d", (int)e->index);
+    case ABFT_EV_DOUBLE_BIT: return snprintf(buf, buflen, "[ECC] double-bit error detected");
+    case ABFT_EV_ROW_SIZE: return snprintf(buf, buflen, "row size constraint violated for row %d", (int)e->index);
+    case ABFT_EV_ROW_ORDER: return snprintf(buf, buflen, "row order constraint violated for row%d", (int)e->index);
+    case ABFT_EV_COL_SIZE: return snprintf(buf, buflen, "column size constraint violated at index %d", (int)e->index);
+    case ABFT_EV_COL_ORDER: return snprintf(buf, buflen, "column order constraint violated at index %d", (int)e->index);
+    case ABFT_EV_CRC_ROW: return snprintf(buf, buflen, "[CRC32C] error detected in row %d", (int)e->index);
+    default: return snprintf(buf, buflen, "unknown event %d", (int)e->kind);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+abft_ctx *abft_cuda_ctx_create(int mode, int device) {
+  if (mode < 0 || mode >= ABFT_MODE_COUNT) {
+    fail(-1, "unknown ABFT mode", __FILE__, __LINE__);
+    return nullptr;
+  }
+  int ndev = abft_cuda_device_count();
+  if (ndev <= 0) {
+    fail(-1, "no CUDA device available (this target has no CPU fallback)", __FILE__, __LINE__);
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) {
+    fail(-1, "device index out of range", __FILE__, __LINE__);
+    return nullptr;
+  }
+  CKP(cudaSetDevice(device));
+  abft_ctx *c = new abft_ctx();
+  c->mode = mode;
+  c->device = device;
+  cudaDeviceProp prop;
+  CKP(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  CKP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CKP(cudaMalloc(&c->d_log, sizeof(DevLog)));
+  CKP(cudaMemset(c->d_log, 0, sizeof(DevLog)));
+  CKP(cudaHostAlloc(&c->h_flag, sizeof(unsigned int) * 16, cudaHostAllocMapped));
+  memset(c->h_flag, 0, sizeof(unsigned int) * 16);
+  CKP(cudaMalloc(&c->d_scalars, sizeof(double) * kNumSlots));
+  CKP(cudaMemset(c->d_scalars, 0, sizeof(double) * kNumSlots));
+  CKP(cudaHostAlloc(&c->h_scalars, sizeof(double) * kNumSlots, cudaHostAllocMapped));
+  memset(c->h_scalars, 0, sizeof(double) * kNumSlots);
+  CKP(cudaMalloc(&c->d_partials, sizeof(double) * kMaxPartials));
+  CKP(cudaMalloc(&c->d_counter, sizeof(unsigned int) * 4));
+  CKP(cudaMemset(c->d_counter, 0, sizeof(unsigned int) * 4));
+  CKP(cudaMalloc(&c->d_loop, sizeof(int) * 4));
+  CKP(cudaMemset(c->d_loop, 0, sizeof(int) * 4));
+  CKP(cudaHostAlloc(&c->h_loop, sizeof(int) * 4, cudaHostAllocMapped));
+  memset(c->h_loop, 0, sizeof(int) * 4);
+  if (ensure_tables(device) != 0) return nullptr;
+  CKP(cudaDeviceSynchronize());
+  return c;
+}
+
+void abft_cuda_ctx_destroy(abft_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_log);
+  cudaFreeHost(c->h_flag);
+  cudaFree(c->d_scalars);
+  cudaFreeHost(c->h_scalars);
+  cudaFree(c->d_partials);
+  cudaFree(c->d_counter);
+  cudaFree(c->d_loop);
+  cudaFreeHost(c->h_loop);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int abft_cuda_ctx_mode(const abft_ctx *c) { return c ? c->mode : -1; }
+
+int abft_cuda_ctx_sync(abft_ctx *c) {
+  REQUIRE(c, "null context");
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+void *abft_cuda_ctx_stream(abft_ctx *c) { return c ? (void *)c->stream : nullptr; }
+uint64_t abft_cuda_launch_count(const abft_ctx *c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------
+// matrix
+// ---------------------------------------------------------------------------
+static void build_tiles(const uint32_t *rowptr, uint32_t n_rows, std::vector<Tile> &tiles) {
+  uint32_t r = 0;
+  while (r < n_rows) {
+    const uint32_t start = rowptr[r];
+    uint32_t e = r;
+    while (e < n_rows && (e - r) < (uint32_t)kTileRows && rowptr[e + 1] >= start &&
+           rowptr[e + 1] - start <= (uint32_t)kTileNnz)
+      e++;
+    if (e == r) e = r + 1;  // one row longer than a tile: streamed in chunks
+    tiles.push_back(Tile{r, e, start, rowptr[e]});
+    r = e;
+  }
+}
+
+abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, const uint32_t *rows,
+                                          const double *values, int n_rows, int nnz, int N_global, int row_offset,
+                                          int64_t nnz_offset) {
+  if (!c || n_rows < 0 || nnz < 0 || N_global < 0 || (nnz > 0 && (!columns || !rows || !values))) {
+    fail(-1, "bad arguments to matrix_create", __FILE__, __LINE__);
+    return nullptr;
+  }
+  if (c->mode >= ABFT_MODE_SED && (unsigned)N_global > (1u << 24)) {
+    fail(-1, "ECC modes keep the check bits in column bits 24..31: N must be <= 2^24", __FILE__, __LINE__);
+    return nullptr;
+  }
+  CKP(cudaSetDevice(c->device));
+  abft_matrix *m = new abft_matrix();
+  const size_t nz = (size_t)std::max(nnz, 1);
+  uint32_t *d_coo_rows = nullptr;
+  CKP(cudaMalloc(&m->view.cols, sizeof(uint32_t) * nz));
+  CKP(cudaMalloc(&m->view.values, sizeof(double) * nz));
+  CKP(cudaMalloc(&m->d_rowptr, sizeof(uint32_t) * ((size_t)n_rows + 1)));
+  CKP(cudaMalloc(&d_coo_rows, sizeof(uint32_t) * nz));
+  if (nnz > 0) {
+    CKP(cudaMemcpyAsync(m->view.cols, columns, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    CKP(cudaMemcpyAsync(d_coo_rows, rows, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    CKP(cudaMemcpyAsync(m->view.values, values, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+  }
+  const int grid = c->num_sms * 8;
+  rowptr_kernel<<<grid, kBlock, 0, c->stream>>>(d_coo_rows, (uint32_t)nnz, (uint32_t)n_rows, (uint32_t)row_offset,
+                                                m->d_rowptr);
+  c->launches++;
+  if (c->mode >= ABFT_MODE_SED && c->mode <= ABFT_MODE_SECDED && nnz > 0) {
+    encode_elements_kernel<<<grid, kBlock, 0, c->stream>>>(c->mode, m->view.cols, m->view.values, (uint32_t)nnz);
+    c->launches++;
+  } else if (c->mode == ABFT_MODE_CRC32C && n_rows > 0) {
+    encode_crc_rows_kernel<<<grid, kBlock, 0, c->stream>>>(m->d_rowptr, m->view.cols, m->view.values, (uint32_t)n_rows);
+    c->launches++;
+  }
+  CKP(cudaGetLastError());
+  // tiles: greedy over the row pointers (host, O(rows))
+  std::vector<uint32_t> h_rowptr((size_t)n_rows + 1);
+  CKP(cudaMemcpyAsync(h_rowptr.data(), m->d_rowptr, sizeof(uint32_t) * ((size_t)n_rows + 1), cudaMemcpyDeviceToHost,
+                      c->stream));
+  CKP(cudaStreamSynchronize(c->stream));
+  CKP(cudaFree(d_coo_rows));
+  std::vector<Tile> tiles;
+  build_tiles(h_rowptr.data(), (uint32_t)n_rows, tiles);
+  m->n_tiles = (int)tiles.size();
+  if (m->n_tiles > kMaxPartials) {
+    fail(-1, "matrix needs more spmv tiles than the reduction buffer holds", __FILE__, __LINE__);
+    return nullptr;
+  }
+  CKP(cudaMalloc(&m->d_tiles, sizeof(Tile) * (size_t)std::max(m->n_tiles, 1)));
+  if (m->n_tiles)
+    CKP(cudaMemcpy(m->d_tiles, tiles.data(), sizeof(Tile) * (size_t)m->n_tiles, cudaMemcpyHostToDevice));
+  m->view.rowptr = m->d_rowptr;
+  m->view.tiles = m->d_tiles;
+  m->view.n_rows = (uint32_t)n_rows;
+  m->view.nnz = (uint32_t)nnz;
+  m->view.n_cols = (uint32_t)N_global;
+  m->view.row_offset = (uint32_t)row_offset;
+  m->view.nnz_offset = (uint32_t)nnz_offset;
+  m->nnz_offset = nnz_offset;
+  return m;
+}
+
+abft_matrix *abft_cuda_matrix_create(abft_ctx *c, const uint32_t *columns, const uint32_t *rows, const double *values,
+                                     int N, int nnz) {
+  return abft_cuda_matrix_create_part(c, columns, rows, values, N, nnz, N, 0, 0);
+}
+
+void abft_cuda_matrix_destroy(abft_ctx *c, abft_matrix *m) {
+  if (!m) return;
+  if (c) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(m->view.cols);
+  cudaFree(m->view.values);
+  cudaFree(m->d_rowptr);
+  cudaFree(m->d_tiles);
+  delete m;
+}
+
+int abft_cuda_matrix_rows(const abft_matrix *m) { return m ? (int)m->view.n_rows : -1; }
+int abft_cuda_matrix_nnz(const abft_matrix *m) { return m ? (int)m->view.nnz : -1; }
+int abft_cuda_matrix_tiles(const abft_matrix *m) { return m ? m->n_tiles : -1; }
+
+int abft_cuda_matrix_read(abft_ctx *c, const abft_matrix *m, uint32_t *cols_out, uint32_t *rowptr_out,
+                          double *values_out) {
+  REQUIRE(c && m, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (cols_out && m->view.nnz) CK(cudaMemcpy(cols_out, m->view.cols, sizeof(uint32_t) * m->view.nnz, cudaMemcpyDeviceToHost));
+  if (values_out && m->view.nnz) CK(cudaMemcpy(values_out, m->view.values, sizeof(double) * m->view.nnz, cudaMemcpyDeviceToHost));
+  if (rowptr_out) CK(cudaMemcpy(rowptr_out, m->d_rowptr, sizeof(uint32_t) * ((size_t)m->view.n_rows + 1), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int abft_cuda_matrix_poke_rowptr(abft_ctx *c, abft_matrix *m, int row, uint32_t value) {
+  REQUIRE(c && m, "null argument");
+  REQUIRE(row >= 0 && (uint32_t)row <= m->view.n_rows, "row out of range");
+  CK(cudaSetDevice(c->device));
+  poke_u32_kernel<<<1, 1, 0, c->stream>>>(m->d_rowptr + row, value);
+  c->launches++;
+  c->epoch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int abft_cuda_matrix_poke_col(abft_ctx *c, abft_matrix *m, int index, uint32_t value) {
+  REQUIRE(c && m, "null argument");
+  REQUIRE(index >= 0 && (uint32_t)index < m->view.nnz, "index out of range");
+  CK(cudaSetDevice(c->device));
+  poke_u32_kernel<<<1, 1, 0, c->stream>>>(m->view.cols + index, value);
+  c->launches++;
+  c->epoch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int abft_cuda_flip_bit(abft_ctx *c, abft_matrix *m, int64_t index, int bit) {
+  REQUIRE(c && m, "null argument");
+  REQUIRE(bit >= 0 && bit < 96, "bit out of range");
+  const int64_t local = index - m->nnz_offset;
+  REQUIRE(local >= 0 && local < (int64_t)m->view.nnz, "element index not in this partition");
+  CK(cudaSetDevice(c->device));
+  flip_bit_kernel<<<1, 32, 0, c->stream>>>(m->view.cols, m->view.values, (uint32_t)local, bit);
+  c->launches++;
+  c->epoch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// vectors
+// ---------------------------------------------------------------------------
+abft_vector *abft_cuda_vector_create(abft_ctx *c, int N) {
+  if (!c || N < 0) {
+    fail(-1, "bad arguments to vector_create", __FILE__, __LINE__);
+    return nullptr;
+  }
+  CKP(cudaSetDevice(c->device));
+  abft_vector *v = new abft_vector();
+  v->N = N;
+  v->owns = true;
+  CKP(cudaMalloc(&v->d, sizeof(double) * (size_t)std::max(N, 1)));
+  CKP(cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)std::max(N, 1), c->stream));
+  return v;
+}
+
+abft_vector *abft_cuda_vector_wrap(abft_ctx *c, double *dev_ptr, int N) {
+  if (!c || N < 0 || (!dev_ptr && N > 0)) {
+    fail(-1, "bad arguments to vector_wrap", __FILE__, __LINE__);
+    return nullptr;
+  }
+  abft_vector *v = new abft_vector();
+  v->N = N;
+  v->d = dev_ptr;
+  v->owns = false;
+  return v;
+}
+
+abft_vector *abft_cuda_vector_view(abft_ctx *c, abft_vector *parent, int offset, int N) {
+  if (!c || !parent || offset < 0 || N < 0 || offset + N > parent->N) {
+    fail(-1, "bad arguments to vector_view", __FILE__, __LINE__);
+    return nullptr;
+  }
+  return abft_cuda_vector_wrap(c, parent->d + offset, N);
+}
+
+void abft_cuda_vector_destroy(abft_ctx *c, abft_vector *v) {
+  if (!v) return;
+  if (c) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->dot_a == v->d || c->dot_b == v->d) c->dot_a = c->dot_b = nullptr;
+  }
+  if (v->owns) cudaFree(v->d);
+  if (v->h_stage) cudaFreeHost(v->h_stage);
+  delete v;
+}
+
+int abft_cuda_vector_len(const abft_vector *v) { return v ? v->N : -1; }
+double *abft_cuda_vector_dev_ptr(abft_vector *v) { return v ? v->d : nullptr; }
+
+double *abft_cuda_vector_map(abft_ctx *c, abft_vector *v) {
+  if (!c || !v) {
+    fail(-1, "null argument", __FILE__, __LINE__);
+    return nullptr;
+  }
+  CKP(cudaSetDevice(c->device));
+  if (!v->h_stage) CKP(cudaHostAlloc(&v->h_stage, sizeof(double) * (size_t)std::max(v->N, 1), cudaHostAllocDefault));
+  if (v->N) CKP(cudaMemcpyAsync(v->h_stage, v->d, sizeof(double) * (size_t)v->N, cudaMemcpyDeviceToHost, c->stream));
+  CKP(cudaStreamSynchronize(c->stream));
+  return v->h_stage;
+}
+
+int abft_cuda_vector_unmap(abft_ctx *c, abft_vector *v, const double *h) {
+  REQUIRE(c && v && (h || v->N == 0), "null argument");
+  CK(cudaSetDevice(c->device));
+  if (v->N) CK(cudaMemcpyAsync(v->d, h, sizeof(double) * (size_t)v->N, cudaMemcpyHostToDevice, c->stream));
+  // pageable sources are staged by the driver before the call returns; a pinned
+  // source (our own staging buffer) must not be reused before the copy ran
+  if (h != v->h_stage) CK(cudaStreamSynchronize(c->stream));
+  c->epoch++;
+  return 0;
+}
+
+int abft_cuda_vector_copy(abft_ctx *c, abft_vector *dst, const abft_vector *src) {
+  REQUIRE(c && dst && src, "null argument");
+  REQUIRE(src->N >= dst->N, "copy_vector: source shorter than destination");
+  CK(cudaSetDevice(c->device));
+  // like the reference, the destination's length decides (CSR/CPUContext.cpp:79)
+  if (dst->N) CK(cudaMemcpyAsync(dst->d, src->d, sizeof(double) * (size_t)dst->N, cudaMemcpyDeviceToDevice, c->stream));
+  c->epoch++;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// hot path
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+template <int MODE>
+static void launch_spmv_mode(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,
+                             const int *active) {
+  LogRef L{c->d_log, c->h_flag};
+  spmv_kernel<MODE><<<m->n_tiles, kBlock, 0, c->stream>>>(m->view, x, y, L, red, active);
+}
+
+static int launch_spmv(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,
+                       const int *active) {
+  if (m->n_tiles == 0) {
+    // no rows: dot(vec, result) over an empty range is 0
+    CK(cudaMemsetAsync(red.dev, 0, sizeof(double), c->stream));
+    *const_cast<double *>(red.host) = 0.0;
+    return 0;
+  }
+  switch (c->mode) {
+    case ABFT_MODE_NONE: launch_spmv_mode<ABFT_MODE_NONE>(c, m, x, y, red, active); break;
+    case ABFT_MODE_CONSTRAINTS: launch_spmv_mode<ABFT_MODE_CONSTRAINTS>(c, m, x, y, red, active); break;
+    case ABFT_MODE_SED: launch_spmv_mode<ABFT_MODE_SED>(c, m, x, y, red, active); break;
+    case ABFT_MODE_SEC7: launch_spmv_mode<ABFT_MODE_SEC7>(c, m, x, y, red, active); break;
+    case ABFT_MODE_SEC8: launch_spmv_mode<ABFT_MODE_SEC8>(c, m, x, y, red, active); break;
+    case ABFT_MODE_SECDED: launch_spmv_mode<ABFT_MODE_SECDED>(c, m, x, y, red, active); break;
+    case ABFT_MODE_CRC32C: launch_spmv_mode<ABFT_MODE_CRC32C>(c, m, x, y, red, active); break;
+    default: return fail(-1, "bad mode", __FILE__, __LINE__);
+  }
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int abft_cuda_spmv(abft_ctx *c, abft_matrix *m, const abft_vector *vec, abft_vector *result) {
+  REQUIRE(c && m && vec && result, "null argument");
+  REQUIRE((uint32_t)result->N >= m->view.n_rows, "spmv: result shorter than the matrix has rows");
+  REQUIRE((uint32_t)vec->N >= m->view.n_cols, "spmv: vector shorter than the matrix has columns");
+  REQUIRE(vec->d != result->d, "spmv: vec and result must not alias");
+  CK(cudaSetDevice(c->device));
+  int rc = launch_spmv(c, m, vec->d, result->d, make_reduce(c, SLOT_SPMV_DOT), nullptr);
+  if (rc) return rc;
+  c->epoch++;
+  // dot(vec[row_offset .. row_offset+n_rows), result[0 .. n_rows)) is now in slot 0
+  c->dot_a = vec->d + m->view.row_offset;
+  c->dot_b = result->d;
+  c->dot_n = (int)m->view.n_rows;
+  c->dot_epoch = c->epoch;
+  return 0;
+}
+
+static int launch_dot(abft_ctx *c, const double *a, const double *b, int N, const ReduceOut &red, const int *active) {
+  const int ok = aligned16(a) && aligned16(b);
+  dot_kernel<<<vec_grid(c, N), kBlock, 0, c->stream>>>(a, b, N, ok, red, active);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int abft_cuda_dot_async(abft_ctx *c, const abft_vector *a, const abft_vector *b, int slot) {
+  REQUIRE(c && a && b, "null argument");
+  REQUIRE(slot >= 0 && slot < kNumSlots, "bad slot");
+  REQUIRE(b->N >= a->N, "dot: second vector shorter than the first");
+  CK(cudaSetDevice(c->device));
+  return launch_dot(c, a->d, b->d, a->N, make_reduce(c, slot), nullptr);
+}
+
+int abft_cuda_dot(abft_ctx *c, const abft_vector *a, const abft_vector *b, double *out) {
+  REQUIRE(c && a && b && out, "null argument");
+  CK(cudaSetDevice(c->device));
+  int slot = SLOT_DOT;
+  const bool fused = c->dot_epoch == c->epoch && a->N == c->dot_n && b->N >= a->N &&
+                     ((a->d == c->dot_a && b->d == c->dot_b) || (a->d == c->dot_b && b->d == c->dot_a));
+  if (fused) {
+    slot = SLOT_SPMV_DOT;  // the spmv just before this call already reduced it
+  } else {
+    int rc = abft_cuda_dot_async(c, a, b, SLOT_DOT);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c->h_scalars[slot];
+  return 0;
+}
+
+static int launch_calc_xr(abft_ctx *c, double *x, double *r, const double *p, const double *w, const ScalarArg &alpha,
+                          bool dev, int N, const ReduceOut &red, const int *active) {
+  const int ok = aligned16(x) && aligned16(r) && aligned16(p) && aligned16(w);
+  if (dev)
+    calc_xr_kernel<true><<<vec_grid(c, N), kBlock, 0, c->stream>>>(x, r, p, w, alpha, N, ok, red, active);
+  else
+    calc_xr_kernel<false><<<vec_grid(c, N), kBlock, 0, c->stream>>>(x, r, p, w, alpha, N, ok, red, active);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int abft_cuda_calc_xr_async(abft_ctx *c, abft_vector *x, abft_vector *r, const abft_vector *p, const abft_vector *w,
+                            double alpha, int slot) {
+  REQUIRE(c && x && r && p && w, "null argument");
+  REQUIRE(slot >= 0 && slot < kNumSlots, "bad slot");
+  REQUIRE(r->N >= x->N && p->N >= x->N && w->N >= x->N, "calc_xr: vector lengths");
+  CK(cudaSetDevice(c->device));
+  ScalarArg a{alpha, nullptr, nullptr};
+  int rc = launch_calc_xr(c, x->d, r->d, p->d, w->d, a, false, x->N, make_reduce(c, slot), nullptr);
+  c->epoch++;
+  return rc;
+}
+
+int abft_cuda_calc_xr(abft_ctx *c, abft_vector *x, abft_vector *r, const abft_vector *p, const abft_vector *w,
+                      double alpha, double *out) {
+  REQUIRE(out, "null argument");
+  int rc = abft_cuda_calc_xr_async(c, x, r, p, w, alpha, SLOT_XR);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c->h_scalars[SLOT_XR];
+  return 0;
+}
+
+static int launch_calc_p(abft_ctx *c, double *p, const double *r, const ScalarArg &beta, bool dev, int N,
+                         const int *active) {
+  const int ok = aligned16(p) && aligned16(r);
+  if (dev)
+    calc_p_kernel<true><<<vec_grid(c, N), kBlock, 0, c->stream>>>(p, r, beta, N, ok, active);
+  else
+    calc_p_kernel<false><<<vec_grid(c, N), kBlock, 0, c->stream>>>(p, r, beta, N, ok, active);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int abft_cuda_calc_p(abft_ctx *c, abft_vector *p, const abft_vector *r, double beta) {
+  REQUIRE(c && p && r, "null argument");
+  REQUIRE(r->N >= p->N, "calc_p: vector lengths");
+  CK(cudaSetDevice(c->device));
+  ScalarArg b{beta, nullptr, nullptr};
+  int rc = launch_calc_p(c, p->d, r->d, b, false, p->N, nullptr);
+  c->epoch++;
+  return rc;
+}
+
+double *abft_cuda_scalar_dev_ptr(abft_ctx *c, int slot) {
+  return (c && slot >= 0 && slot < kNumSlots) ? c->d_scalars + slot : nullptr;
+}
+double abft_cuda_scalar_host(abft_ctx *c, int slot) {
+  return (c && slot >= 0 && slot < kNumSlots) ? c->h_scalars[slot] : 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// fault reporting
+// ---------------------------------------------------------------------------
+int abft_cuda_events_pending(abft_ctx *c) { return (c && *c->h_flag) ? 1 : 0; }
+
+int abft_cuda_poll_events(abft_ctx *c, abft_event *out, int cap, int *fatal) {
+  if (fatal) *fatal = 0;
+  if (!c) return -1;
+  if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    fail(-1, "poll_events: sync failed", __FILE__, __LINE__);
+    return -1;
+  }
+  if (*c->h_flag == 0) return 0;
+  unsigned int count = 0;
+  if (cudaMemcpy(&count, &c->d_log->count, sizeof count, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  count = std::min(count, (unsigned)kLogCap);
+  std::vector<abft_event> ev(count);
+  if (count && cudaMemcpy(ev.data(), c->d_log->ev, sizeof(abft_event) * count, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  cudaMemset(c->d_log, 0, sizeof(unsigned int) * 2);
+  *c->h_flag = 0;
+
+  // serial order of the reference: rows ascending; within a row the row checks
+  // come before its elements, elements ascending (CSR/CPUContext.cpp:166-206)
+  const bool cons = c->mode == ABFT_MODE_CONSTRAINTS;
+  auto key = [&](const abft_event &e, uint64_t &k1, int &k2, uint64_t &k3) {
+    const bool rowev = e.kind == ABFT_EV_ROW_SIZE || e.kind == ABFT_EV_ROW_ORDER || e.kind == ABFT_EV_CRC_ROW;
+    if (cons) {
+      k1 = rowev ? e.index : e.bit;  // element events of CONSTRAINTS carry their row in `bit`
+      k2 = rowev ? 0 : 1;
+      k3 = e.index;
+    } else {
+      k1 = e.index;
+      k2 = 0;
+      k3 = e.bit;
+    }
+  };
+  std::sort(ev.begin(), ev.end(), [&](const abft_event &a, const abft_event &b) {
+    uint64_t a1, a3, b1, b3;
+    int a2, b2;
+    key(a, a1, a2, a3);
+    key(b, b1, b2, b3);
+    if (a1 != b1) return a1 < b1;
+    if (a2 != b2) return a2 < b2;
+    if (a3 != b3) return a3 < b3;
+    return a.kind < b.kind;
+  });
+  int n = 0;
+  for (unsigned int i = 0; i < count && n < cap; i++) {
+    abft_event e = ev[i];
+    if (cons && (e.kind == ABFT_EV_COL_SIZE || e.kind == ABFT_EV_COL_ORDER)) e.bit = 0;
+    // a fault that persists is found again by every spmv until it is polled: report it once
+    if (n > 0 && out[n - 1].kind == e.kind && out[n - 1].index == e.index && out[n - 1].bit == e.bit) continue;
+    out[n++] = e;
+    if (abft_cuda_event_is_fatal(e.kind)) {
+      if (fatal) *fatal = 1;
+      break;  // the reference exit(1)s here
+    }
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------
+// device-resident CG loop
+// ---------------------------------------------------------------------------
+int abft_cuda_cg_solve(abft_ctx *c, abft_matrix *A, const abft_vector *b, abft_vector *x, abft_vector *r,
+                       abft_vector *p, abft_vector *w, int max_itrs, double conv_threshold, int check_every,
+                       double *rr_out) {
+  if (!c || !A || !b || !x || !r || !p || !w) {
+    fail(-1, "null argument", __FILE__, __LINE__);
+    return -1;
+  }
+  const int N = (int)A->view.n_rows;
+  if (A->view.row_offset != 0 || A->view.n_cols != (uint32_t)N || b->N < N || x->N < N || r->N < N || p->N < N ||
+      w->N < N) {
+    fail(-1, "cg_solve needs a whole (unpartitioned) matrix and vectors of its size", __FILE__, __LINE__);
+    return -1;
+  }
+  if (check_every < 1) check_every = 1;
+  if (cudaSetDevice(c->device) != cudaSuccess) return -1;
+  cudaStream_t s = c->stream;
+  int *flag0 = c->d_loop, *iters = c->d_loop + 2;
+  cudaMemsetAsync(c->d_loop, 0, sizeof(int) * 4, s);
+  c->h_loop[0] = 0;
+  c->h_loop[1] = 0;
+  // r = b ; p = r ; rr = r.r   (cg.cpp:87-91)
+  cudaMemcpyAsync(r->d, b->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s);
+  cudaMemcpyAsync(p->d, r->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s);
+  {
+    ReduceOut red = make_reduce(c, SLOT_RR0);
+    red.active = flag0;  // iteration 0 reads flag[0]
+    red.iters = iters;
+    red.threshold = conv_threshold;
+    red.max_itrs = max_itrs;
+    red.bump_iters = 0;
+    if (launch_dot(c, r->d, r->d, N, red, nullptr)) return -1;
+  }
+  c->epoch++;
+  int launched = 0;
+  int done_iters = 0;
+  bool active = true;
+  while (active && launched < max_itrs) {
+    const int batch = std::min(check_every, max_itrs - launched);
+    for (int j = 0; j < batch; j++, launched++) {
+      const int q = launched & 1;
+      const int *flag_cur = c->d_loop + q;
+      int *flag_next = c->d_loop + (q ^ 1);
+      const double *rr_cur = c->d_scalars + (q ? SLOT_RR1 : SLOT_RR0);
+      const int slot_new = q ? SLOT_RR0 : SLOT_RR1;
+      // w = A p, pw = p.w
+      if (launch_spmv(c, A, p->d, w->d, make_reduce(c, SLOT_SPMV_DOT), flag_cur)) return -1;
+      // alpha = rr / pw ; x += alpha p ; r -= alpha w ; rr_new = r.r
+      ReduceOut red = make_reduce(c, slot_new);
+      red.active = flag_next;
+      red.iters = iters;
+      red.threshold = conv_threshold;
+      red.max_itrs = max_itrs;
+      red.bump_iters = 1;
+      ScalarArg alpha{0.0, rr_cur, c->d_scalars + SLOT_SPMV_DOT};
+      if (launch_calc_xr(c, x->d, r->d, p->d, w->d, alpha, true, N, red, flag_cur)) return -1;
+      // beta = rr_new / rr ; p = r + beta p
+      ScalarArg beta{0.0, c->d_scalars + slot_new, rr_cur};
+      if (launch_calc_p(c, p->d, r->d, beta, true, N, flag_cur)) return -1;
+    }
+    // read back progress: iterations done and whether the next one would run
+    cudaMemcpyAsync(c->h_loop, c->d_loop + 2, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(c->h_loop + 1, c->d_loop + (launched & 1), sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      fail(-1, "cg_solve: stream sync failed", __FILE__, __LINE__);
+      return -1;
+    }
+    done_iters = c->h_loop[0];
+    active = c->h_loop[1] != 0;
+    if (*c->h_flag) {
+      // a fault was logged; fatal ones stop the solve like the reference's exit(1)
+      unsigned int count = 0;
+      cudaMemcpy(&count, &c->d_log->count, sizeof count, cudaMemcpyDeviceToHost);
+      count = std::min(count, (unsigned)kLogCap);
+      std::vector<abft_event> ev(count);
+      if (count) cudaMemcpy(ev.data(), c->d_log->ev, sizeof(abft_event) * count, cudaMemcpyDeviceToHost);
+      for (auto &e : ev)
+        if (abft_cuda_event_is_fatal(e.kind)) {
+          c->epoch++;
+          return -2;
+        }
+    }
+  }
+  c->epoch++;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+  if (rr_out) *rr_out = c->h_scalars[(done_iters & 1) ? SLOT_RR1 : SLOT_RR0];
+  return done_iters;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+/*
+ * abft_cuda.h -- C ABI of the B200-native (sm_100a) CUDA target for the CSR CG
+ * hot path of abft-sparse-cg.
+ *
+ * This is the drop-in boundary.  The reference's boundary is the C++ plugin
+ * class CGContext (CGContext.h:8-67); its twelve pure virtuals map 1:1 onto
+ * the entry points below, and abft-sparse-cg_b200/host/CUDAContext.cpp is the
+ * thin CGContext subclass that forwards to them and registers
+ * ("cuda", <mode>) in the reference's own registry (CGContext.h:55-63), so the
+ * unmodified cg.cpp runs `-t cuda -m <mode>`.  INTEGRATION.md shows the
+ * reference-side binding.
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  All host pointers
+ * are ordinary (pageable or pinned) host memory unless a name says `dev`.
+ * Unless noted, functions return 0 on success and a non-zero CUDA error code
+ * otherwise; abft_cuda_last_error() returns the text.  There is NO CPU
+ * fallback: with no usable CUDA device every call fails.
+ *
+ * Threading: like the reference (single host thread, one context per
+ * process, CGContext.h / cg.cpp:42-154) a context must be driven by one
+ * thread at a time.  All work of a context is ordered on one CUDA stream.
+ */
+#ifndef ABFT_CUDA_H
+#define ABFT_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABFT_CUDA_ABI_VERSION 1
+
+/* ABFT modes == the `-m` strings registered by CSR/CPUContext.cpp:413-421,
+ * plus crc32c (defined by this repository). */
+enum abft_mode {
+  ABFT_MODE_NONE = 0,
+  ABFT_MODE_CONSTRAINTS = 1,
+  ABFT_MODE_SED = 2,
+  ABFT_MODE_SEC7 = 3,
+  ABFT_MODE_SEC8 = 4,
+  ABFT_MODE_SECDED = 5,
+  ABFT_MODE_CRC32C = 6,
+  ABFT_MODE_COUNT = 7
+};
+
+/* One record per message the reference printf()s from inside spmv
+ * (CSR/CPUContext.cpp:175,180,190,197,233,278,324,331,380,387,398). */
+enum abft_event_kind {
+  ABFT_EV_SED_DETECTED = 1,     /* "[ECC] error detected at index %d"              fatal */
+  ABFT_EV_CORRECTED_BIT = 2,    /* "[ECC] corrected bit %u at index %d"                  */
+  ABFT_EV_CORRECTED_PARITY = 3, /* "[ECC] corrected overall parity bit at index %d"      */
+  ABFT_EV_DOUBLE_BIT = 4,       /* "[ECC] double-bit error detected"               fatal */
+  ABFT_EV_ROW_SIZE = 5,         /* "row size constraint violated for row %d"       fatal */
+  ABFT_EV_ROW_ORDER = 6,        /* "row order constraint violated for row%d"       fatal */
+  ABFT_EV_COL_SIZE = 7,         /* "column size constraint violated at index %d"   fatal */
+  ABFT_EV_COL_ORDER = 8,        /* "column order constraint violated at index %d"  fatal */
+  ABFT_EV_CRC_ROW = 9           /* "[CRC32C] error detected in row %d"             fatal */
+};
+
+typedef struct abft_event {
+  int32_t kind;   /* enum abft_event_kind */
+  uint32_t index; /* GLOBAL CSR element index (row number for ROW_* / CRC_ROW) */
+  uint32_t bit;   /* element bit 0..95 for CORRECTED_BIT (0..63 value, 64..95 column) */
+} abft_event;
+
+typedef struct abft_ctx abft_ctx;       /* replaces a CGContext instance            */
+typedef struct abft_matrix abft_matrix; /* replaces cg_matrix (CSR/CPUContext.h:11-18) */
+typedef struct abft_vector abft_vector; /* replaces cg_vector (CSR/CPUContext.h:5-9)   */
+
+/* ---- library ---- */
+int abft_cuda_abi_version(void);
+const char *abft_cuda_last_error(void);
+const char *abft_cuda_mode_name(int mode);    /* "none", "constraints", ... or NULL */
+int abft_cuda_mode_from_name(const char *s);  /* -1 if unknown */
+int abft_cuda_device_count(void);             /* 0 when no CUDA device is usable */
+/* reference message text of an event, no trailing newline; returns strlen */
+int abft_cuda_format_event(const abft_event *e, char *buf, int buflen);
+int abft_cuda_event_is_fatal(int kind);
+
+/* ---- context: CGContext::create(target, mode) (CGContext.cpp:9-25) ---- */
+abft_ctx *abft_cuda_ctx_create(int mode, int device); /* NULL on failure */
+void abft_cuda_ctx_destroy(abft_ctx *ctx);
+int abft_cuda_ctx_mode(const abft_ctx *ctx);
+int abft_cuda_ctx_sync(abft_ctx *ctx); /* wait for everything queued on the context */
+void *abft_cuda_ctx_stream(abft_ctx *ctx); /* the context's cudaStream_t */
+
+/* ---- matrix: create_matrix / destroy_matrix (CSR/CPUContext.cpp:11-52) ----
+ * Triplets sorted by (row, col), 0-based (what cg.cpp:394-418 passes).  The
+ * arrays are deep-copied (the caller frees them at once, cg.cpp:420-422); the
+ * COO->CSR conversion and the per-element / per-row ECC encode
+ * (generate_ecc_bits, CSR/CPUContext.cpp:209-212,247-250,291-295,347-351) run
+ * on the device.  ECC modes need N <= 2^24 (column index is 24 bits,
+ * CSR/CPUContext.cpp:238,282,338,404). */
+abft_matrix *abft_cuda_matrix_create(abft_ctx *ctx, const uint32_t *columns, const uint32_t *rows,
+                                     const double *values, int N, int nnz);
+/* Row partition [row_offset, row_offset+n_rows) of an N_global-column matrix
+ * (multi-GPU): `rows` are GLOBAL row numbers, `columns` stay
+ * GLOBAL so the ECC words are bit-identical to the single-GPU encoding;
+ * nnz_offset = global index of this partition's first element (used for the
+ * `index` of reported events and for flip routing). */
+abft_matrix *abft_cuda_matrix_create_part(abft_ctx *ctx, const uint32_t *columns, const uint32_t *rows,
+                                          const double *values, int n_rows, int nnz, int N_global,
+                                          int row_offset, int64_t nnz_offset);
+void abft_cuda_matrix_destroy(abft_ctx *ctx, abft_matrix *mat);
+int abft_cuda_matrix_rows(const abft_matrix *mat);
+int abft_cuda_matrix_nnz(const abft_matrix *mat);
+/* copy the stored (encoded) CSR arrays back; any pointer may be NULL.
+ * cols_out[nnz], rowptr_out[n_rows+1], values_out[nnz].  Test/debug aid. */
+int abft_cuda_matrix_read(abft_ctx *ctx, const abft_matrix *mat, uint32_t *cols_out, uint32_t *rowptr_out,
+                          double *values_out);
+/* overwrite one row pointer (fault injection into rows[] for the CONSTRAINTS checks) */
+int abft_cuda_matrix_poke_rowptr(abft_ctx *ctx, abft_matrix *mat, int row, uint32_t value);
+int abft_cuda_matrix_poke_col(abft_ctx *ctx, abft_matrix *mat, int index, uint32_t value);
+
+/* ---- vectors (CSR/CPUContext.cpp:54-80) ---- */
+abft_vector *abft_cuda_vector_create(abft_ctx *ctx, int N); /* zero-filled */
+/* non-owning vector over caller-managed DEVICE memory (e.g. a torch tensor) */
+abft_vector *abft_cuda_vector_wrap(abft_ctx *ctx, double *dev_ptr, int N);
+/* non-owning window [offset, offset+N) of another vector */
+abft_vector *abft_cuda_vector_view(abft_ctx *ctx, abft_vector *parent, int offset, int N);
+void abft_cuda_vector_destroy(abft_ctx *ctx, abft_vector *v);
+int abft_cuda_vector_len(const abft_vector *v);
+double *abft_cuda_vector_dev_ptr(abft_vector *v);
+/* map_vector: device->host copy into a pinned staging buffer owned by the
+ * vector; the pointer stays valid until unmap.  Several vectors may be mapped
+ * at once (cg.cpp:66-74).  NULL on failure. */
+double *abft_cuda_vector_map(abft_ctx *ctx, abft_vector *v);
+/* unmap_vector: host->device copy of all N entries from `h` (the pointer map
+ * returned, or any host buffer of N doubles). */
+int abft_cuda_vector_unmap(abft_ctx *ctx, abft_vector *v, const double *h);
+int abft_cuda_vector_copy(abft_ctx *ctx, abft_vector *dst, const abft_vector *src);
+
+/* ---- the hot path (cg.cpp:97-112) ---- */
+/* spmv: result = A * vec, ABFT check/correct of the context's mode fused into
+ * the element stream (CSR/CPUContext.cpp:115-133,162-207,214-245,252-289,
+ * 297-345,353-411).  Asynchronous.  Faults found are queued and surface at the
+ * next abft_cuda_poll_events().  Also leaves dot(vec, result) on the device so
+ * the abft_cuda_dot(vec, result) that cg.cpp:100 issues next costs no pass. */
+int abft_cuda_spmv(abft_ctx *ctx, abft_matrix *mat, const abft_vector *vec, abft_vector *result);
+/* dot (CSR/CPUContext.cpp:82-90): blocks until the value is on the host */
+int abft_cuda_dot(abft_ctx *ctx, const abft_vector *a, const abft_vector *b, double *out);
+/* calc_xr (CSR/CPUContext.cpp:92-105): x += alpha p; r -= alpha w; *out = r.r */
+int abft_cuda_calc_xr(abft_ctx *ctx, abft_vector *x, abft_vector *r, const abft_vector *p,
+                      const abft_vector *w, double alpha, double *out);
+/* calc_p (CSR/CPUContext.cpp:107-113): p = r + beta p.  Asynchronous. */
+int abft_cuda_calc_p(abft_ctx *ctx, abft_vector *p, const abft_vector *r, double beta);
+
+/* Asynchronous halves of dot / calc_xr for multi-GPU use: the partial result
+ * stays on the device (and in a pinned host slot after abft_cuda_ctx_sync) so
+ * the caller can all-reduce it.  slot in [0, 8). */
+int abft_cuda_dot_async(abft_ctx *ctx, const abft_vector *a, const abft_vector *b, int slot);
+int abft_cuda_calc_xr_async(abft_ctx *ctx, abft_vector *x, abft_vector *r, const abft_vector *p,
+                            const abft_vector *w, double alpha, int slot);
+double *abft_cuda_scalar_dev_ptr(abft_ctx *ctx, int slot);  /* device address of slot */
+double abft_cuda_scalar_host(abft_ctx *ctx, int slot);       /* value after a sync */
+#define ABFT_SLOT_SPMV_DOT 0  /* where spmv leaves dot(vec, result) */
+
+/* ---- fault injection: the RMW of inject_bitflip (CSR/CPUContext.cpp:150-157).
+ * `index` is a GLOBAL element index, bit 0..63 flips the value, 64..95 the
+ * column word.  The caller draws rand() (one for the index, one per flip,
+ * CSR/CPUContext.cpp:137,148) so that sequences match the reference. */
+int abft_cuda_flip_bit(abft_ctx *ctx, abft_matrix *mat, int64_t index, int bit);
+
+/* ---- fault reporting ----
+ * Waits for queued work, then moves the pending events, sorted in the
+ * reference's serial order (ascending row / element index), into out[0..cap).
+ * Returns the number written (<= cap), or -1 on a CUDA error.  *fatal (may be
+ * NULL) is set to 1 if one of them is fatal; events after the first fatal one
+ * are dropped, as the reference would have exit(1)ed there. */
+int abft_cuda_poll_events(abft_ctx *ctx, abft_event *out, int cap, int *fatal);
+/* cheap host-side check (no sync): non-zero if events may be pending */
+int abft_cuda_events_pending(abft_ctx *ctx);
+
+/* ---- device-resident CG loop (cg.cpp:83-118 without the two host round trips
+ * per iteration).  Runs copy r=b, p=r, rr=r.r and then iterations until
+ * max_itrs or rr <= conv_threshold, scalars (alpha, beta, rr) staying on the
+ * device; the convergence flag is read back every `check_every` iterations,
+ * kernels of iterations past convergence are no-ops, so the iteration count
+ * and the vectors equal those of the host-driven loop.  Returns iterations
+ * run (>= 0), or -1 on error / -2 if a fatal fault event is pending. */
+int abft_cuda_cg_solve(abft_ctx *ctx, abft_matrix *A, const abft_vector *b, abft_vector *x, abft_vector *r,
+                       abft_vector *p, abft_vector *w, int max_itrs, double conv_threshold, int check_every,
+                       double *rr_out);
+
+/* ---- introspection for bench.py / tests ---- */
+/* number of kernels this library has launched on the context since creation */
+uint64_t abft_cuda_launch_count(const abft_ctx *ctx);
+/* tiles of the spmv work decomposition */
+int abft_cuda_matrix_tiles(const abft_matrix *mat);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABFT_CUDA_H */
