@@ -80,6 +80,7 @@ struct abft_ctx {
   int *d_loop = nullptr;            // [0],[1] = active flags (ring of 2), [2] = iterations done
   int *h_loop = nullptr;            // mapped pinned mirror: [0] = iterations, [1] = next-active
   uint64_t launches = 0;
+  int spmv_ctas_per_sm = 0;  // resident CTAs of this mode's spmv kernel (set at first launch)
   // fused dot(vec, result) left behind by the last spmv
   const double *dot_a = nullptr, *dot_b = nullptr;
   int dot_n = 0;
@@ -250,11 +251,25 @@ static void build_tiles(const uint32_t *rowptr, uint32_t n_rows, std::vector<Til
   while (r < n_rows) {
     const uint32_t start = rowptr[r];
     uint32_t e = r;
+    uint32_t max_len = 0;
     while (e < n_rows && (e - r) < (uint32_t)kTileRows && rowptr[e + 1] >= start &&
-           rowptr[e + 1] - start <= (uint32_t)kTileNnz)
+           rowptr[e + 1] - start <= (uint32_t)kTileNnz) {
+      max_len = std::max(max_len, rowptr[e + 1] - rowptr[e]);
       e++;
-    if (e == r) e = r + 1;  // one row longer than a tile: streamed in chunks
-    tiles.push_back(Tile{r, e, start, rowptr[e]});
+    }
+    uint32_t info;
+    if (e == r) {
+      e = r + 1;  // one row longer than a tile: streamed from global memory in chunks
+      info = 1u | kTileLongRow;
+    } else {
+      const uint32_t nrows = e - r, nnz = rowptr[e] - start;
+      info = nrows;
+      // thread-per-row pays max_len steps, element-parallel pays nnz/kBlock (+ a light row phase):
+      // rows of similar length (every stencil matrix) go thread-per-row
+      const uint32_t mean_up = (nnz + nrows - 1) / nrows;
+      if (max_len <= 2 * mean_up + 4) info |= kTileRegular;
+    }
+    tiles.push_back(Tile{r, start, rowptr[e], info});
     r = e;
   }
 }
@@ -274,10 +289,14 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
   abft_matrix *m = new abft_matrix();
   const size_t nz = (size_t)std::max(nnz, 1);
   uint32_t *d_coo_rows = nullptr;
-  CKP(cudaMalloc(&m->view.cols, sizeof(uint32_t) * nz));
-  CKP(cudaMalloc(&m->view.values, sizeof(double) * nz));
-  CKP(cudaMalloc(&m->d_rowptr, sizeof(uint32_t) * ((size_t)n_rows + 1)));
+  // +16 elements of padding: the TMA bulk copies of a tile round its window out to 16-byte granules
+  CKP(cudaMalloc(&m->view.cols, sizeof(uint32_t) * (nz + 16)));
+  CKP(cudaMalloc(&m->view.values, sizeof(double) * (nz + 16)));
+  CKP(cudaMalloc(&m->d_rowptr, sizeof(uint32_t) * ((size_t)n_rows + 1 + 16)));
   CKP(cudaMalloc(&d_coo_rows, sizeof(uint32_t) * nz));
+  CKP(cudaMemsetAsync(m->view.cols + nz, 0, sizeof(uint32_t) * 16, c->stream));
+  CKP(cudaMemsetAsync(m->view.values + nz, 0, sizeof(double) * 16, c->stream));
+  CKP(cudaMemsetAsync(m->d_rowptr + (size_t)n_rows + 1, 0, sizeof(uint32_t) * 16, c->stream));
   if (nnz > 0) {
     CKP(cudaMemcpyAsync(m->view.cols, columns, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
     CKP(cudaMemcpyAsync(d_coo_rows, rows, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
@@ -313,6 +332,7 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
     CKP(cudaMemcpy(m->d_tiles, tiles.data(), sizeof(Tile) * (size_t)m->n_tiles, cudaMemcpyHostToDevice));
   m->view.rowptr = m->d_rowptr;
   m->view.tiles = m->d_tiles;
+  m->view.n_tiles = (uint32_t)m->n_tiles;
   m->view.n_rows = (uint32_t)n_rows;
   m->view.nnz = (uint32_t)nnz;
   m->view.n_cols = (uint32_t)N_global;
@@ -480,11 +500,26 @@ int abft_cuda_vector_copy(abft_ctx *c, abft_vector *dst, const abft_vector *src)
 // ---------------------------------------------------------------------------
 }  // extern "C"
 
+// persistent grid: SMs x resident CTAs of this mode's kernel (never more CTAs than tiles)
+template <int MODE>
+static int spmv_resident_ctas(abft_ctx *c) {
+  if (c->spmv_ctas_per_sm == 0) {
+    cudaFuncSetAttribute(spmv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvDynSmem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_kernel<MODE>, kBlock, kSpmvDynSmem) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 1;
+    c->spmv_ctas_per_sm = per_sm;
+  }
+  return c->spmv_ctas_per_sm * c->num_sms;
+}
+
 template <int MODE>
 static void launch_spmv_mode(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,
                              const int *active) {
   LogRef L{c->d_log, c->h_flag};
-  spmv_kernel<MODE><<<m->n_tiles, kBlock, 0, c->stream>>>(m->view, x, y, L, red, active);
+  const int grid = std::min(m->n_tiles, spmv_resident_ctas<MODE>(c));
+  spmv_kernel<MODE><<<grid, kBlock, kSpmvDynSmem, c->stream>>>(m->view, x, y, L, red, active);
 }
 
 static int launch_spmv(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,

@@ -1,119 +1,180 @@
 // spmv.cuh -- CSR SpMV with the per-element ABFT check/correct fused into the
-// coalesced column/value stream (reference: CSR/CPUContext.cpp:115-133 NONE,
-// 162-207 CONSTRAINTS, 214-245 SED, 252-289 SEC7, 297-345 SEC8, 353-411 SECDED;
-// CRC32C is this repository's own mode).
+// column/value stream (reference: CSR/CPUContext.cpp:115-133 NONE, 162-207
+// CONSTRAINTS, 214-245 SED, 252-289 SEC7, 297-345 SEC8, 353-411 SECDED; CRC32C is
+// this repository's own mode).
 //
-// Work decomposition ("tiles", built once in create_matrix): a tile is a run of
-// whole rows with at most kTileNnz non-zeros and at most kBlock rows; one CTA
-// per tile.
-//   element phase  every lane owns elements e = u*kBlock + tid of the tile's
-//                  nnz range: coalesced streaming loads of cols/values, the
-//                  mode's ECC check (the owning lane corrects + writes back +
-//                  logs), gather of vec[col], product -> shared memory.
-//   row phase      thread r sums the products of row r from shared memory IN
-//                  ELEMENT ORDER with separate multiply and add, i.e. exactly
-//                  the reference's `tmp += values[i] * vec[col]` (no FMA in the
-//                  reference build), so result[] is bit-identical to the CPU
-//                  target; then the fused dot(vec, result) partial.
-// A row longer than kTileNnz is a tile of its own, streamed in chunks with a
-// tree reduction (not bit-identical to the sequential CPU sum; within 1e-10).
-// CONSTRAINTS element events carry their global row in `bit` (the host orders
-// them against ROW_* events with it and clears it before reporting).
+// B200 design (DESIGN.md "spmv kernel"):
+//  * Work unit = "tile": a run of whole rows with <= kTileNnz non-zeros and
+//    <= kTileRows rows, built once in create_matrix.
+//  * Persistent CTAs (grid = SMs x resident CTAs), tile t of CTA b is b + t*grid so
+//    the whole chip sweeps the matrix front together and vec[] stays L2-resident.
+//  * The tile's cols / values / row pointers are contiguous in memory: one elected
+//    thread streams them into shared memory with TMA bulk copies (cp.async.bulk +
+//    mbarrier complete_tx), kStages deep, so HBM latency is hidden behind the ECC
+//    arithmetic of the previous tile instead of behind occupancy.
+//  * Regular tiles (row lengths within 2x of the mean; every stencil matrix):
+//    thread r walks row r in shared memory -- check, gather vec[col] (lanes = rows,
+//    so a banded matrix gathers coalesced), multiply, add -- in ELEMENT ORDER with
+//    separate multiply and add, i.e. exactly the reference's
+//    `tmp += values[i] * vec[col]`: result[] is bit-identical to the CPU target.
+//  * Irregular tiles (power-law rows): element-parallel check + product into shared
+//    memory, then thread r adds row r's products in element order (same bits).
+//  * A row longer than kTileNnz is a tile of its own, streamed from global memory in
+//    chunks with a tree reduction (not bit-identical to the sequential sum; < 1e-10).
+//  * The owning lane corrects a faulty element in registers, writes it back to
+//    global memory and logs the event; dot(vec, result) is reduced in the epilogue.
+// CONSTRAINTS element events carry their global row in `bit` (the host orders them
+// against ROW_* events with it and clears it before reporting).
 #pragma once
 #include "common.cuh"
 #include "ecc.cuh"
 
 namespace abft {
 
-constexpr int kEpt = 8;                      // elements per thread per tile
-constexpr int kTileNnz = kBlock * kEpt;      // 2048
-constexpr int kTileRows = kBlock;            // 256
+constexpr int kTileNnz = 2048;
+constexpr int kTileRows = kBlock;  // 256: one row per thread
+constexpr int kStages = 2;
+
+constexpr uint32_t kTileRegular = 1u << 16;  // info flag: thread-per-row path
+constexpr uint32_t kTileLongRow = 1u << 17;  // info flag: single row > kTileNnz, streamed
 
 struct Tile {
-  uint32_t row_begin, row_end;  // local rows
-  uint32_t nnz_begin, nnz_end;  // local element indices
+  uint32_t row_begin;  // local row
+  uint32_t nnz_begin;  // local element indices
+  uint32_t nnz_end;
+  uint32_t info;       // bits 0..15 number of rows, flags above
 };
 
 struct MatView {
-  const uint32_t *rowptr;  // [n_rows+1] local element indices
-  uint32_t *cols;          // [nnz] column word incl. check bits
-  double *values;          // [nnz]
+  const uint32_t *rowptr;  // [n_rows+1 (+pad)] local element indices
+  uint32_t *cols;          // [nnz (+pad)] column word incl. check bits
+  double *values;          // [nnz (+pad)]
   const Tile *tiles;
+  uint32_t n_tiles;
   uint32_t n_rows, nnz;
   uint32_t n_cols;      // global N: bound for the gather
   uint32_t row_offset;  // global index of local row 0
   uint32_t nnz_offset;  // global index of local element 0 (for reported indices)
 };
 
+// one pipeline stage of staged tile data (windows start at 16-byte aligned indices)
+struct __align__(16) StageBuf {
+  double vals[kTileNnz + 2];
+  uint32_t cols[kTileNnz + 8];
+  uint32_t rptr[kTileRows + 8];
+};
+constexpr size_t kSpmvDynSmem = sizeof(StageBuf) * kStages;
+
+// ---- PTX: mbarrier + TMA bulk copy (global -> shared) -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ void split_value(double v, uint32_t &w0, uint32_t &w1) {
   w0 = (uint32_t)__double2loint(v);
   w1 = (uint32_t)__double2hiint(v);
 }
 
-// Slow path shared by SEC7 / SEC8 / SECDED: undo the flip the syndrome points
-// at (CSR/CPUContext.cpp:272-278, 320-324, 376-380).  A multi-bit fault can
-// yield bit >= 96, where the reference writes past its 12-byte element (UB);
-// here the bit is reported and the element left alone.
-__device__ __noinline__ void correct_from_syndrome(uint32_t &w0, uint32_t &w1, uint32_t &col, uint32_t syndrome,
-                                                   uint32_t gindex, LogRef L) {
-  uint32_t bit = flipped_bit(syndrome);
-  if (bit < 32) w0 ^= 1u << bit;
-  else if (bit < 64) w1 ^= 1u << (bit - 32);
-  else if (bit < 96) col ^= 1u << (bit - 64);
-  log_event(L, ABFT_EV_CORRECTED_BIT, gindex, bit);
-}
-
-// The per-element check of one mode.  Returns true if the element was modified
-// and must be written back.  `poison` is set when a detect-only fault makes the
-// column untrustworthy.
+// ---- the per-element check ------------------------------------------------------------
+// Slow path (a fault was seen): everything by value / in registers, nothing on the stack.
+// Returns {w0, w1, col, changed}.  SEC7 / SEC8 / SECDED undo the flip the syndrome points
+// at (CSR/CPUContext.cpp:272-278, 320-334, 376-390); a multi-bit fault can yield bit >= 96,
+// where the reference writes past its 12-byte element (UB): the bit is reported and the
+// element left alone.
 template <int MODE>
-__device__ __forceinline__ bool check_element(uint32_t &w0, uint32_t &w1, uint32_t &col, uint32_t gindex,
-                                              const LogRef &L) {
+__device__ __noinline__ uint4 handle_fault(uint32_t w0, uint32_t w1, uint32_t col, uint32_t gindex, DevLog *log,
+                                           volatile unsigned int *flag) {
+  const LogRef L{log, flag};
+  uint32_t changed = 0;
   if (MODE == ABFT_MODE_SED) {
-    if (overall_parity(w0, w1, col)) log_event(L, ABFT_EV_SED_DETECTED, gindex, 0);
-    return false;
-  }
-  if (MODE == ABFT_MODE_SEC7) {
-    if (syndrome7_any(w0, w1, col)) {
-      correct_from_syndrome(w0, w1, col, syndrome7(w0, w1, col), gindex, L);
-      return true;
-    }
-    return false;
-  }
-  if (MODE == ABFT_MODE_SEC8) {
-    if (overall_parity(w0, w1, col)) {
-      uint32_t s = syndrome7(w0, w1, col);
-      if (s) correct_from_syndrome(w0, w1, col, s, gindex, L);
-      else { col ^= 1u << 24; log_event(L, ABFT_EV_CORRECTED_PARITY, gindex, 0); }
-      return true;
-    }
-    return false;
-  }
-  if (MODE == ABFT_MODE_SECDED) {
+    log_event(L, ABFT_EV_SED_DETECTED, gindex, 0);
+  } else {
     const uint32_t odd = overall_parity(w0, w1, col);
-    const uint32_t syn = syndrome7_any(w0, w1, col);
-    if (odd | syn) {
-      if (odd) {
-        uint32_t s = syndrome7(w0, w1, col);
-        if (s) correct_from_syndrome(w0, w1, col, s, gindex, L);
-        else { col ^= 1u << 24; log_event(L, ABFT_EV_CORRECTED_PARITY, gindex, 0); }
-        return true;
+    const uint32_t s = syndrome7(w0, w1, col);
+    const bool correct = (MODE == ABFT_MODE_SEC7) ? (s != 0) : (odd != 0);
+    if (correct) {
+      if (s) {
+        const uint32_t bit = flipped_bit(s);
+        if (bit < 32) w0 ^= 1u << bit;
+        else if (bit < 64) w1 ^= 1u << (bit - 32);
+        else if (bit < 96) col ^= 1u << (bit - 64);
+        log_event(L, ABFT_EV_CORRECTED_BIT, gindex, bit);
+      } else {
+        col ^= 1u << 24;
+        log_event(L, ABFT_EV_CORRECTED_PARITY, gindex, 0);
       }
+      changed = 1;
+    } else if (MODE == ABFT_MODE_SECDED && s) {
       log_event(L, ABFT_EV_DOUBLE_BIT, gindex, 0);
     }
-    return false;
   }
-  return false;
+  return make_uint4(w0, w1, col, changed);
+}
+
+// bit 0 set iff the element fails the mode's fast check
+template <int MODE>
+__device__ __forceinline__ uint32_t element_suspect(uint32_t w0, uint32_t w1, uint32_t col) {
+  if (MODE == ABFT_MODE_SED || MODE == ABFT_MODE_SEC8) return overall_parity(w0, w1, col);
+  if (MODE == ABFT_MODE_SEC7) return syndrome7_any(w0, w1, col);
+  if (MODE == ABFT_MODE_SECDED) return (overall_parity(w0, w1, col) | syndrome7_any(w0, w1, col)) & 1u;
+  return 0;
 }
 
 template <int MODE>
 struct ModeTraits {
+  static constexpr bool per_element_ecc = MODE >= ABFT_MODE_SED && MODE <= ABFT_MODE_SECDED;
   static constexpr bool masks_column = MODE >= ABFT_MODE_SED;  // check bits in column bits 24..31
-  static constexpr bool keeps_cols = MODE == ABFT_MODE_CONSTRAINTS || MODE == ABFT_MODE_CRC32C;
 };
 
-// CRC-32C of one 12-byte element appended to a running (raw) state; slicing-by-4
-// tables in shared memory: tab[s*256 + b].
+// check (and repair) one element, gather vec[col], return the rounded product
+template <int MODE>
+__device__ __forceinline__ double element_product(uint32_t cw, double v, uint32_t li, const MatView &A,
+                                                  const double *__restrict__ x, const LogRef &L) {
+  if (ModeTraits<MODE>::per_element_ecc) {
+    uint32_t w0, w1;
+    split_value(v, w0, w1);
+    if (element_suspect<MODE>(w0, w1, cw)) {
+      const uint4 f = handle_fault<MODE>(w0, w1, cw, A.nnz_offset + li, L.log, L.flag);
+      if (f.w) {
+        cw = f.z;
+        v = __hiloint2double((int)f.y, (int)f.x);
+        A.cols[li] = cw;
+        A.values[li] = v;
+      }
+    }
+  }
+  const uint32_t col = ModeTraits<MODE>::masks_column ? (cw & 0x00FFFFFFu) : cw;
+  // a column no check caught can point outside vec[] (the reference reads out of bounds: UB)
+  const double xv = (col < A.n_cols) ? __ldg(x + col) : 0.0;
+  return __dmul_rn(v, xv);
+}
+
+// CRC-32C of one 32-bit word appended to a running (raw) state; slicing-by-4 tables
+// tab[s*256 + b] in shared memory.
 __device__ __forceinline__ uint32_t crc_word(uint32_t crc, uint32_t w, const uint32_t *tab) {
   const uint32_t x = crc ^ w;
   return tab[768 + (x & 0xFF)] ^ tab[512 + ((x >> 8) & 0xFF)] ^ tab[256 + ((x >> 16) & 0xFF)] ^ tab[x >> 24];
@@ -122,194 +183,200 @@ __device__ __forceinline__ uint32_t crc_word(uint32_t crc, uint32_t w, const uin
 __device__ uint32_t g_crc_tab[1024];  // filled by the host at library init
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, (MODE == ABFT_MODE_CRC32C) ? 2 : 3)
+__global__ void __launch_bounds__(kBlock, (MODE == ABFT_MODE_CRC32C) ? 3 : 4)
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
             const int *__restrict__ active) {
-  __shared__ __align__(16) double s_prod[kTileNnz];
-  __shared__ uint32_t s_col[ModeTraits<MODE>::keeps_cols ? kTileNnz : 1];
-  __shared__ double s_val[(MODE == ABFT_MODE_CRC32C) ? kTileNnz : 1];
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  StageBuf *stage = reinterpret_cast<StageBuf *>(dyn_smem);
+  __shared__ __align__(8) uint64_t s_full[kStages];
+  __shared__ Tile s_tile[kStages];
   __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? 1024 : 1];
   __shared__ double s_warp[kBlock / 32];
 
   if (active && *active == 0) return;  // device-resident loop already converged
 
   const int tid = threadIdx.x;
-  const Tile t = A.tiles[blockIdx.x];
-  const uint32_t nrows = t.row_end - t.row_begin;
-  const uint32_t n = t.nnz_end - t.nnz_begin;
+  const uint32_t G = gridDim.x;
+  const uint32_t n_my = (A.n_tiles > blockIdx.x) ? (A.n_tiles - blockIdx.x + G - 1) / G : 0;
 
-  if (MODE == ABFT_MODE_CRC32C) {
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(&s_full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (MODE == ABFT_MODE_CRC32C)
     for (int i = tid; i < 1024; i += kBlock) s_crc[i] = g_crc_tab[i];
-    __syncthreads();
-  }
+  __syncthreads();
 
-  // row pointers of my row, requested early so their latency overlaps the stream
-  uint32_t rs = 0, re = 0;
-  const bool has_row = (uint32_t)tid < nrows;
-  if (has_row) {
-    rs = A.rowptr[t.row_begin + tid];
-    re = A.rowptr[t.row_begin + tid + 1];
+  // producer (thread 0): stream tile `t` into stage `s`
+  auto issue = [&](int s, const Tile &t) {
+    StageBuf &B = stage[s];
+    const uint32_t nrows = t.info & 0xFFFFu;
+    const uint32_t rb = t.row_begin & ~3u;
+    const uint32_t rbytes = ((t.row_begin + nrows + 1 + 3) & ~3u) * 4u - rb * 4u;
+    uint32_t cbytes = 0, vbytes = 0;
+    const uint32_t cb = t.nnz_begin & ~3u, vb = t.nnz_begin & ~1u;
+    if (!(t.info & kTileLongRow) && t.nnz_end > t.nnz_begin) {
+      cbytes = ((t.nnz_end + 3) & ~3u) * 4u - cb * 4u;
+      vbytes = ((t.nnz_end + 1) & ~1u) * 8u - vb * 8u;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&s_full[s], rbytes + cbytes + vbytes);
+    bulk_g2s(B.rptr, A.rowptr + rb, rbytes, &s_full[s]);
+    if (cbytes) {
+      bulk_g2s(B.cols, A.cols + cb, cbytes, &s_full[s]);
+      bulk_g2s(B.vals, A.values + vb, vbytes, &s_full[s]);
+    }
+  };
+
+  Tile ahead{};  // descriptor of the next tile to issue (thread 0 only)
+  if (tid == 0) {
+    for (uint32_t j = 0; j + 1 < (uint32_t)kStages && j < n_my; j++) {
+      const Tile t = A.tiles[blockIdx.x + j * G];
+      s_tile[j] = t;
+      issue((int)j, t);
+    }
+    if ((uint32_t)(kStages - 1) < n_my) ahead = A.tiles[blockIdx.x + (kStages - 1) * G];
   }
+  __syncthreads();
 
   double dot_part = 0.0;
 
-  if (n <= (uint32_t)kTileNnz) {
-    // ---------------- element phase ----------------
-    uint32_t c[kEpt];
-    double v[kEpt];
-#pragma unroll
-    for (int u = 0; u < kEpt; u++) {
-      const uint32_t e = u * kBlock + tid;
-      c[u] = 0;
-      v[u] = 0.0;
-      if (e < n) {
-        c[u] = ld_stream(A.cols + t.nnz_begin + e);
-        v[u] = ld_stream(A.values + t.nnz_begin + e);
+  for (uint32_t it = 0; it < n_my; it++) {
+    const int st = (int)(it % kStages);
+    // refill the stage the previous iteration released
+    if (tid == 0) {
+      const uint32_t j = it + kStages - 1;
+      if (j < n_my) {
+        s_tile[j % kStages] = ahead;
+        issue((int)(j % kStages), ahead);
+        if (j + 1 < n_my) ahead = A.tiles[blockIdx.x + (j + 1) * G];  // latency overlaps this tile's work
       }
     }
-    double xv[kEpt];
-#pragma unroll
-    for (int u = 0; u < kEpt; u++) {
-      const uint32_t e = u * kBlock + tid;
-      xv[u] = 0.0;
-      if (e < n) {
-        if (MODE >= ABFT_MODE_SED && MODE <= ABFT_MODE_SECDED) {
-          uint32_t w0, w1;
-          split_value(v[u], w0, w1);
-          if (check_element<MODE>(w0, w1, c[u], A.nnz_offset + t.nnz_begin + e, L)) {
-            v[u] = __hiloint2double((int)w1, (int)w0);
-            A.cols[t.nnz_begin + e] = c[u];
-            A.values[t.nnz_begin + e] = v[u];
-          }
-        }
-        const uint32_t col = ModeTraits<MODE>::masks_column ? (c[u] & 0x00FFFFFFu) : c[u];
-        if (col < A.n_cols) xv[u] = __ldg(x + col);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kEpt; u++) {
-      const uint32_t e = u * kBlock + tid;
-      if (e < n) {
-        s_prod[e] = __dmul_rn(v[u], xv[u]);
-        if (ModeTraits<MODE>::keeps_cols) s_col[e] = c[u];
-        if (MODE == ABFT_MODE_CRC32C) s_val[e] = v[u];
-      }
-    }
-    __syncthreads();
+    mbar_wait(&s_full[st], (it / kStages) & 1u);
+    const Tile t = s_tile[st];
+    const StageBuf &B = stage[st];
+    const uint32_t nrows = t.info & 0xFFFFu;
+    const uint32_t n = t.nnz_end - t.nnz_begin;
+    const uint32_t rb = t.row_begin & ~3u, cb = t.nnz_begin & ~3u, vb = t.nnz_begin & ~1u;
+    const bool has_row = (uint32_t)tid < nrows;
+    const uint32_t row = t.row_begin + tid;
 
-    // ---------------- row phase ----------------
-    if (has_row) {
-      const uint32_t row = t.row_begin + tid;
-      bool row_ok = true;
-      if (MODE == ABFT_MODE_CONSTRAINTS) {
-        // CSR/CPUContext.cpp:173-182
-        if (re > A.nnz) { log_event(L, ABFT_EV_ROW_SIZE, A.row_offset + row, 0); row_ok = false; }
-        else if (re < rs) { log_event(L, ABFT_EV_ROW_ORDER, A.row_offset + row, 0); row_ok = false; }
-      } else {
-        // other modes trust rows[] like the reference; clamp so a bad pointer cannot fault
-        rs = min(max(rs, t.nnz_begin), t.nnz_end);
-        re = min(max(re, rs), t.nnz_end);
-      }
-      double sum = 0.0;
-      if (row_ok) {
-        if (MODE == ABFT_MODE_CONSTRAINTS) {
-          for (uint32_t i = rs; i < re; i++) {
-            // elements normally sit in the tile's shared-memory window; a corrupted
-            // row pointer can send the row outside it, then go to global memory
-            const bool in = (i >= t.nnz_begin) && (i < t.nnz_end);
-            const uint32_t col = in ? s_col[i - t.nnz_begin] : A.cols[i];
-            if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + row); break; }
-            if (i < re - 1) {
-              const bool in2 = (i + 1 >= t.nnz_begin) && (i + 1 < t.nnz_end);
-              const uint32_t nxt = in2 ? s_col[i + 1 - t.nnz_begin] : A.cols[i + 1];
-              if (nxt <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + row); break; }
-            }
-            const double prod = in ? s_prod[i - t.nnz_begin] : __dmul_rn(A.values[i], __ldg(x + col));
-            sum = __dadd_rn(sum, prod);
+    if (t.info & kTileLongRow) {
+      // ---------------- one long row: stream it from global memory in chunks ----------------
+      double acc = 0.0;
+      bool flagged = false;
+      for (uint32_t base = 0; base < n; base += kBlock) {
+        const uint32_t e = base + tid;
+        if (e < n) {
+          const uint32_t i = t.nnz_begin + e;
+          const uint32_t cw = ld_stream(A.cols + i);
+          const double val = ld_stream(A.values + i);
+          if (MODE == ABFT_MODE_CONSTRAINTS && !flagged) {
+            if (cw >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + t.row_begin); flagged = true; }
+            else if (e + 1 < n && A.cols[i + 1] <= cw) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + t.row_begin); flagged = true; }
           }
+          acc = __dadd_rn(acc, element_product<MODE>(cw, val, i, A, x, L));
+        }
+      }
+      if (MODE == ABFT_MODE_CRC32C && tid == 0) {
+        // long rows are rare: one thread walks the row for the CRC
+        uint32_t crc = 0xFFFFFFFFu, stored = 0;
+        for (uint32_t e = 0; e < n; e++) {
+          const uint32_t i = t.nnz_begin + e;
+          const uint32_t cw = A.cols[i];
+          uint32_t w0, w1;
+          split_value(A.values[i], w0, w1);
+          if (e < 4) stored |= (cw >> 24) << (8 * e);
+          crc = crc_word(crc, w0, s_crc);
+          crc = crc_word(crc, w1, s_crc);
+          crc = crc_word(crc, cw & 0x00FFFFFFu, s_crc);
+        }
+        if ((crc ^ 0xFFFFFFFFu) != stored) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + t.row_begin, 0);
+      }
+      const double total = block_sum(acc, s_warp);
+      if (tid == 0) {
+        y[t.row_begin] = total;
+        dot_part = __dadd_rn(dot_part, __dmul_rn(total, x[A.row_offset + t.row_begin]));
+      }
+    } else {
+      const bool row_mapped = (t.info & kTileRegular) || MODE == ABFT_MODE_CRC32C || MODE == ABFT_MODE_CONSTRAINTS;
+      if (!row_mapped) {
+        // ---------------- irregular tile, element phase: product -> shared memory (in place) ----------------
+        double *prod = const_cast<double *>(B.vals);
+        for (uint32_t e = tid; e < n; e += kBlock) {
+          const uint32_t li = t.nnz_begin + e;
+          prod[li - vb] = element_product<MODE>(B.cols[li - cb], B.vals[li - vb], li, A, x, L);
+        }
+        __syncthreads();
+      }
+      if (has_row) {
+        uint32_t rs = B.rptr[row - rb], re = B.rptr[row + 1 - rb];
+        bool row_ok = true;
+        if (MODE == ABFT_MODE_CONSTRAINTS) {
+          // CSR/CPUContext.cpp:173-182
+          if (re > A.nnz) { log_event(L, ABFT_EV_ROW_SIZE, A.row_offset + row, 0); row_ok = false; }
+          else if (re < rs) { log_event(L, ABFT_EV_ROW_ORDER, A.row_offset + row, 0); row_ok = false; }
         } else {
-          if (MODE == ABFT_MODE_CRC32C) {
+          // other modes trust rows[] like the reference; clamp so a bad pointer cannot fault
+          rs = min(max(rs, t.nnz_begin), t.nnz_end);
+          re = min(max(re, rs), t.nnz_end);
+        }
+        double sum = 0.0;
+        if (row_ok) {
+          if (MODE == ABFT_MODE_CONSTRAINTS) {
+            for (uint32_t i = rs; i < re; i++) {
+              // elements normally sit in the staged window; a corrupted row pointer can send the
+              // row outside it, then go to global memory (i < nnz was checked above)
+              const bool in = (i >= t.nnz_begin) && (i < t.nnz_end);
+              const uint32_t col = in ? B.cols[i - cb] : A.cols[i];
+              if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + row); break; }
+              if (i < re - 1) {
+                const bool in2 = (i + 1 >= t.nnz_begin) && (i + 1 < t.nnz_end);
+                const uint32_t nxt = in2 ? B.cols[i + 1 - cb] : A.cols[i + 1];
+                if (nxt <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + row); break; }
+              }
+              const double val = in ? B.vals[i - vb] : A.values[i];
+              sum = __dadd_rn(sum, __dmul_rn(val, __ldg(x + col)));
+            }
+          } else if (MODE == ABFT_MODE_CRC32C) {
             const uint32_t len = re - rs;
+            uint32_t crc = 0xFFFFFFFFu, stored = 0;
             bool bad = false;
-            if (len >= 4) {
-              uint32_t crc = 0xFFFFFFFFu, stored = 0;
-              for (uint32_t i = rs; i < re; i++) {
-                const uint32_t k = i - t.nnz_begin;
-                uint32_t w0, w1;
-                split_value(s_val[k], w0, w1);
-                const uint32_t cw = s_col[k];
+            for (uint32_t i = rs; i < re; i++) {
+              const uint32_t cw = B.cols[i - cb];
+              const double val = B.vals[i - vb];
+              uint32_t w0, w1;
+              split_value(val, w0, w1);
+              if (len >= 4) {
                 if (i - rs < 4) stored |= (cw >> 24) << (8 * (i - rs));
                 crc = crc_word(crc, w0, s_crc);
                 crc = crc_word(crc, w1, s_crc);
                 crc = crc_word(crc, cw & 0x00FFFFFFu, s_crc);
+              } else {
+                // too short to hold 32 CRC bits: SECDED check byte per element, detect-only
+                if ((overall_parity(w0, w1, cw) | syndrome7_any(w0, w1, cw)) & 1u) bad = true;
               }
-              bad = (crc ^ 0xFFFFFFFFu) != stored;
-            } else {
-              for (uint32_t i = rs; i < re; i++) {
-                const uint32_t k = i - t.nnz_begin;
-                uint32_t w0, w1;
-                split_value(s_val[k], w0, w1);
-                if (overall_parity(w0, w1, s_col[k]) | syndrome7_any(w0, w1, s_col[k])) bad = true;
-              }
+              sum = __dadd_rn(sum, element_product<MODE>(cw, val, i, A, x, L));
             }
+            if (len >= 4 && (crc ^ 0xFFFFFFFFu) != stored) bad = true;
             if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
-          }
-          for (uint32_t i = rs - t.nnz_begin; i < re - t.nnz_begin; i++) sum = __dadd_rn(sum, s_prod[i]);
-        }
-      }
-      y[row] = sum;
-      dot_part = __dmul_rn(sum, x[A.row_offset + row]);
-    }
-  } else {
-    // ---------------- one long row: stream it in chunks ----------------
-    // (tile builder guarantees nrows == 1 here)
-    double acc = 0.0;
-    bool flagged = false;
-    uint32_t crc_dummy = 0;
-    (void)crc_dummy;
-    for (uint32_t base = 0; base < n; base += kBlock) {
-      const uint32_t e = base + tid;
-      if (e < n) {
-        const uint32_t i = t.nnz_begin + e;
-        uint32_t cw = ld_stream(A.cols + i);
-        double val = ld_stream(A.values + i);
-        if (MODE >= ABFT_MODE_SED && MODE <= ABFT_MODE_SECDED) {
-          uint32_t w0, w1;
-          split_value(val, w0, w1);
-          if (check_element<MODE>(w0, w1, cw, A.nnz_offset + i, L)) {
-            val = __hiloint2double((int)w1, (int)w0);
-            A.cols[i] = cw;
-            A.values[i] = val;
+          } else if (t.info & kTileRegular) {
+            // ---------------- regular tile: thread-per-row straight from the staged stream ----------------
+#pragma unroll 4
+            for (uint32_t i = rs; i < re; i++)
+              sum = __dadd_rn(sum, element_product<MODE>(B.cols[i - cb], B.vals[i - vb], i, A, x, L));
+          } else {
+            // ---------------- irregular tile, row phase: add the products in element order ----------------
+#pragma unroll 4
+            for (uint32_t i = rs; i < re; i++) sum = __dadd_rn(sum, B.vals[i - vb]);
           }
         }
-        const uint32_t col = ModeTraits<MODE>::masks_column ? (cw & 0x00FFFFFFu) : cw;
-        if (MODE == ABFT_MODE_CONSTRAINTS && !flagged) {
-          if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + t.row_begin); flagged = true; }
-          else if (e + 1 < n && A.cols[i + 1] <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + t.row_begin); flagged = true; }
-        }
-        if (col < A.n_cols) acc = __dadd_rn(acc, __dmul_rn(val, __ldg(x + col)));
+        y[row] = sum;
+        dot_part = __dadd_rn(dot_part, __dmul_rn(sum, x[A.row_offset + row]));
       }
     }
-    if (MODE == ABFT_MODE_CRC32C && tid == 0) {
-      // long rows are rare: one thread walks the row (global memory) for the CRC
-      uint32_t crc = 0xFFFFFFFFu, stored = 0;
-      for (uint32_t e = 0; e < n; e++) {
-        const uint32_t i = t.nnz_begin + e;
-        const uint32_t cw = A.cols[i];
-        uint32_t w0, w1;
-        split_value(A.values[i], w0, w1);
-        if (e < 4) stored |= (cw >> 24) << (8 * e);
-        crc = crc_word(crc, w0, s_crc);
-        crc = crc_word(crc, w1, s_crc);
-        crc = crc_word(crc, cw & 0x00FFFFFFu, s_crc);
-      }
-      if ((crc ^ 0xFFFFFFFFu) != stored) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + t.row_begin, 0);
-    }
-    const double total = block_sum(acc, s_warp);
-    if (tid == 0) {
-      y[t.row_begin] = total;
-      dot_part = __dmul_rn(total, x[A.row_offset + t.row_begin]);
-    }
+    __syncthreads();  // everyone is done with stage `st`: it may be refilled
   }
 
   // fused dot(vec, result): CTA partial, then the grid-wide deterministic sum

@@ -38,8 +38,8 @@ __global__ void bench(unsigned long long *cycles, unsigned *sink, unsigned seed)
       if (OP == DFMA) asm volatile("fma.rn.f64 %0, %0, %1, %0;" : "+d"(d[c]) : "d"(d[(c + 1) % kChains]));
       if (OP == DADD) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[c]) : "d"(d[(c + 1) % kChains]));
       if (OP == DMUL) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(d[c]) : "d"(d[(c + 1) % kChains]));
-      if (OP == LDS32) { unsigned a = (x[c] & 1023u) * 4u; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x[c]) : "r"(a)); }
-      if (OP == LDS64) { unsigned a = (x[c] & 511u) * 8u; unsigned lo, hi; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a)); x[c] = lo ^ hi; }
+      if (OP == LDS32) { x[c] = ((volatile unsigned *)smem)[x[c] & 1023u]; }
+      if (OP == LDS64) { const volatile unsigned long long *q = (const volatile unsigned long long *)smem; unsigned long long v = q[x[c] & 511u]; x[c] = (unsigned)v ^ (unsigned)(v >> 32); }
       if (OP == MIX_SECDED) {
         // the per-element fast path: 21 masked-xor LOP3, 8 POPC, 4 OR-combines
         unsigned w0 = x[c], w1 = x[(c + 1) % kChains], w2 = x[(c + 2) % kChains], acc = 0;
