@@ -268,6 +268,7 @@ static void build_tiles(const uint32_t *rowptr, uint32_t n_rows, std::vector<Til
       // rows of similar length (every stencil matrix) go thread-per-row
       const uint32_t mean_up = (nnz + nrows - 1) / nrows;
       if (max_len <= 2 * mean_up + 4) info |= kTileRegular;
+      info |= std::min(max_len, 0xFFFu) << kTileMaxLenShift;
     }
     tiles.push_back(Tile{r, start, rowptr[e], info});
     r = e;

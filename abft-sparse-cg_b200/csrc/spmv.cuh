@@ -37,12 +37,13 @@ constexpr int kStages = 2;
 
 constexpr uint32_t kTileRegular = 1u << 16;  // info flag: thread-per-row path
 constexpr uint32_t kTileLongRow = 1u << 17;  // info flag: single row > kTileNnz, streamed
+constexpr int kTileMaxLenShift = 18;         // info bits 18..29: longest row of the tile
 
 struct Tile {
   uint32_t row_begin;  // local row
   uint32_t nnz_begin;  // local element indices
   uint32_t nnz_end;
-  uint32_t info;       // bits 0..15 number of rows, flags above
+  uint32_t info;       // bits 0..15 number of rows, 16..17 flags, 18..29 longest row
 };
 
 struct MatView {
@@ -144,6 +145,21 @@ __device__ __forceinline__ uint32_t element_suspect(uint32_t w0, uint32_t w1, ui
   return 0;
 }
 
+// like element_suspect but without the final `& 1`: callers OR these over a whole row and
+// test bit 0 once
+template <int MODE>
+__device__ __forceinline__ uint32_t element_suspect_bits(uint32_t w0, uint32_t w1, uint32_t col) {
+  if (MODE == ABFT_MODE_SED || MODE == ABFT_MODE_SEC8) return __popc(w0 ^ w1 ^ col);
+  if (MODE == ABFT_MODE_SEC7 || MODE == ABFT_MODE_SECDED) {
+    uint32_t a = __popc(masked<1>(w0, w1, col)) | __popc(masked<2>(w0, w1, col)) | __popc(masked<3>(w0, w1, col));
+    uint32_t b = __popc(masked<4>(w0, w1, col)) | __popc(masked<5>(w0, w1, col)) | __popc(masked<6>(w0, w1, col));
+    uint32_t c = a | b | __popc(masked<7>(w0, w1, col));
+    if (MODE == ABFT_MODE_SECDED) c |= __popc(w0 ^ w1 ^ col);
+    return c;
+  }
+  return 0;
+}
+
 template <int MODE>
 struct ModeTraits {
   static constexpr bool per_element_ecc = MODE >= ABFT_MODE_SED && MODE <= ABFT_MODE_SECDED;
@@ -171,6 +187,41 @@ __device__ __forceinline__ double element_product(uint32_t cw, double v, uint32_
   // a column no check caught can point outside vec[] (the reference reads out of bounds: UB)
   const double xv = (col < A.n_cols) ? __ldg(x + col) : 0.0;
   return __dmul_rn(v, xv);
+}
+
+// Fast walk over up to LEN consecutive elements of one row, fully unrolled: all shared-memory
+// loads first, then all checks and gathers (LEN independent loads in flight), then the products
+// are added to `sum` in element order.  No per-element branch: the checks only OR their verdict
+// into `suspect`; the caller re-walks the row on the careful path if bit 0 ends up set (rare).
+template <int MODE, int LEN>
+__device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_t count, const uint32_t *s_cols,
+                                             const double *s_vals, uint32_t n_cols, const double *__restrict__ x,
+                                             uint32_t &suspect) {
+  uint32_t c[LEN];
+  double v[LEN], xv[LEN];
+#pragma unroll
+  for (int k = 0; k < LEN; k++) {
+    c[k] = 0;   // an absent element reads as {+0.0, column 0}: a valid code word in every mode
+    v[k] = 0.0;
+    if ((uint32_t)k < count) {
+      c[k] = s_cols[first + k];
+      v[k] = s_vals[first + k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LEN; k++) {
+    if (ModeTraits<MODE>::per_element_ecc) {
+      uint32_t w0, w1;
+      split_value(v[k], w0, w1);
+      suspect |= element_suspect_bits<MODE>(w0, w1, c[k]);
+    }
+    const uint32_t col = ModeTraits<MODE>::masks_column ? (c[k] & 0x00FFFFFFu) : c[k];
+    xv[k] = (col < n_cols) ? __ldg(x + col) : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < LEN; k++)
+    if ((uint32_t)k < count) sum = __dadd_rn(sum, __dmul_rn(v[k], xv[k]));
+  return sum;
 }
 
 // CRC-32C of one 32-bit word appended to a running (raw) state; slicing-by-4 tables
@@ -363,9 +414,25 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
             if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
           } else if (t.info & kTileRegular) {
             // ---------------- regular tile: thread-per-row straight from the staged stream ----------------
-#pragma unroll 4
-            for (uint32_t i = rs; i < re; i++)
-              sum = __dadd_rn(sum, element_product<MODE>(B.cols[i - cb], B.vals[i - vb], i, A, x, L));
+            const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the CTA
+            const uint32_t len = re - rs;
+            const uint32_t *sc = B.cols + (rs - cb);
+            const double *sv = B.vals + (rs - vb);
+            uint32_t suspect = 0;
+            if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
+            else if (max_len == 5) sum = walk_chunk<MODE, 5>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
+            else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
+            else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
+            else
+              for (uint32_t base = 0; base < max_len; base += 8)
+                sum = walk_chunk<MODE, 8>(sum, base, len > base ? len - base : 0u, sc, sv, A.n_cols, x, suspect);
+            if (suspect & 1u) {
+              // a check tripped somewhere in this row: walk it again element by element, repairing /
+              // reporting as the mode demands (the owning thread writes the element back)
+              sum = 0.0;
+              for (uint32_t i = rs; i < re; i++)
+                sum = __dadd_rn(sum, element_product<MODE>(B.cols[i - cb], B.vals[i - vb], i, A, x, L));
+            }
           } else {
             // ---------------- irregular tile, row phase: add the products in element order ----------------
 #pragma unroll 4
