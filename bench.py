@@ -63,7 +63,7 @@ class ClockSampler:
         self.lines, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -95,7 +95,7 @@ class ClockSampler:
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        busy = [s for s, p in zip(sm, power) if p > 250.0] or sm
+        busy = [s for s, p in zip(sm, power) if p > 300.0] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
@@ -287,8 +287,8 @@ def main():
 
     # ---- value: K iterations, operands resident in HBM ----
     start_solve()
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # sampled from the warm-up on: the timed region is short
     iterate(max(args.warmup, 3))
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = ctx.launch_count()
     ms_total = timed(lambda: iterate(args.steps))
     launches = ctx.launch_count() - l0
