@@ -8,9 +8,10 @@ The Python here is only a ctypes mirror of that ABI for tests and bench.py:
     capi      raw ctypes binding of every symbol in include/abft_cuda.h
     context   CUDAContext: same method names / argument meaning as CGContext
     matgen    synthetic Poisson / power-law matrices in cg.cpp's triplet order
+    dist      row partition + exchange plan + the multi-GPU CG loop over the dist_* entry points
 
 The directory name is not an importable identifier; load it with
 ``pkg_loader.load()`` at the repository root.
 """
-from . import capi, context, matgen  # noqa: F401
+from . import capi, context, dist, matgen  # noqa: F401
 from .context import CUDAContext, FatalFault, MODES  # noqa: F401

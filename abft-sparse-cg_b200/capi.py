@@ -31,6 +31,10 @@ SYMBOLS = [
     "abft_cuda_dot_async", "abft_cuda_calc_xr_async", "abft_cuda_scalar_dev_ptr", "abft_cuda_scalar_host",
     "abft_cuda_flip_bit", "abft_cuda_poll_events", "abft_cuda_events_pending",
     "abft_cuda_cg_solve", "abft_cuda_launch_count", "abft_cuda_matrix_tiles",
+    "abft_cuda_comm_create", "abft_cuda_comm_destroy", "abft_cuda_comm_window_handle", "abft_cuda_vector_ipc_handle",
+    "abft_cuda_comm_window_ptr", "abft_cuda_comm_attach_self", "abft_cuda_comm_attach_peer",
+    "abft_cuda_comm_attach_peer_ptrs", "abft_cuda_comm_set_plan", "abft_cuda_dist_push", "abft_cuda_dist_calc_p",
+    "abft_cuda_dist_spmv", "abft_cuda_dist_dot", "abft_cuda_dist_calc_xr",
 ]
 
 
@@ -106,6 +110,21 @@ def load():
     sig("abft_cuda_events_pending", i32, vp)
     sig("abft_cuda_cg_solve", i32, vp, vp, vp, vp, vp, vp, vp, i32, f64, i32, f64p)
     sig("abft_cuda_launch_count", C.c_uint64, vp)
+    i32p = C.POINTER(C.c_int)
+    sig("abft_cuda_comm_create", vp, vp, i32, i32)
+    sig("abft_cuda_comm_destroy", None, vp, vp)
+    sig("abft_cuda_comm_window_handle", i32, vp, vp, C.c_char_p)
+    sig("abft_cuda_vector_ipc_handle", i32, vp, vp, C.c_char_p)
+    sig("abft_cuda_comm_window_ptr", vp, vp)
+    sig("abft_cuda_comm_attach_self", i32, vp, vp, vp)
+    sig("abft_cuda_comm_attach_peer", i32, vp, vp, i32, C.c_char_p, C.c_char_p)
+    sig("abft_cuda_comm_attach_peer_ptrs", i32, vp, vp, i32, vp, vp, i32)
+    sig("abft_cuda_comm_set_plan", i32, vp, vp, i32p, i32p, C.c_uint, i32)
+    sig("abft_cuda_dist_push", i32, vp, vp, vp)
+    sig("abft_cuda_dist_calc_p", i32, vp, vp, vp, vp, f64)
+    sig("abft_cuda_dist_spmv", i32, vp, vp, vp, vp, vp)
+    sig("abft_cuda_dist_dot", i32, vp, vp, vp, vp, f64p)
+    sig("abft_cuda_dist_calc_xr", i32, vp, vp, vp, vp, vp, vp, f64, f64p)
     _lib = L
     return L
 

@@ -88,6 +88,19 @@ struct abft_ctx {
   uint64_t epoch = 1;  // bumped by every call that writes vector data
 };
 
+struct abft_comm {
+  int rank = 0, world = 1;
+  CommWindow *win[kMaxRanks] = {};     // device-visible pointers; win[rank] is local
+  double *peer_vec[kMaxRanks] = {};    // peers' full-length exchange vectors
+  void *ipc_opened[2 * kMaxRanks] = {};  // pointers obtained from cudaIpcOpenMemHandle
+  int n_ipc = 0;
+  int push_lo[kMaxRanks] = {}, push_hi[kMaxRanks] = {};
+  unsigned int wait_mask = 0;
+  int row0 = 0;
+  unsigned int seq = 0;    // reductions issued so far (same on every rank)
+  unsigned int epoch = 0;  // pushes issued so far
+};
+
 static const char *kModeNames[ABFT_MODE_COUNT] = {"none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"};
 
 static bool g_tables_ready[64] = {false};
@@ -102,8 +115,14 @@ static int ensure_tables(int device) {
   return 0;
 }
 
-static ReduceOut make_reduce(abft_ctx *c, int slot) {
+static ReduceOut make_reduce(abft_ctx *c, int slot, abft_comm *comm = nullptr) {
   ReduceOut r{};
+  if (comm && comm->world > 1) {
+    for (int s = 0; s < comm->world; s++) r.peers.win[s] = comm->win[s];
+    r.peers.world = comm->world;
+    r.peers.rank = comm->rank;
+    r.peers.seq = ++comm->seq;
+  }
   r.partials = c->d_partials;
   r.counter = c->d_counter;
   r.dev = c->d_scalars + slot;
@@ -517,14 +536,14 @@ static int spmv_resident_ctas(abft_ctx *c) {
 
 template <int MODE>
 static void launch_spmv_mode(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,
-                             const int *active) {
+                             const int *active, const WaitSpec &wait) {
   LogRef L{c->d_log, c->h_flag};
   const int grid = std::min(m->n_tiles, spmv_resident_ctas<MODE>(c));
-  spmv_kernel<MODE><<<grid, kBlock, kSpmvDynSmem, c->stream>>>(m->view, x, y, L, red, active);
+  spmv_kernel<MODE><<<grid, kBlock, kSpmvDynSmem, c->stream>>>(m->view, x, y, L, red, active, wait);
 }
 
 static int launch_spmv(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,
-                       const int *active) {
+                       const int *active, const WaitSpec &wait = WaitSpec{nullptr, 0u, 0u}) {
   if (m->n_tiles == 0) {
     // no rows: dot(vec, result) over an empty range is 0
     CK(cudaMemsetAsync(red.dev, 0, sizeof(double), c->stream));
@@ -532,13 +551,13 @@ static int launch_spmv(abft_ctx *c, const abft_matrix *m, const double *x, doubl
     return 0;
   }
   switch (c->mode) {
-    case ABFT_MODE_NONE: launch_spmv_mode<ABFT_MODE_NONE>(c, m, x, y, red, active); break;
-    case ABFT_MODE_CONSTRAINTS: launch_spmv_mode<ABFT_MODE_CONSTRAINTS>(c, m, x, y, red, active); break;
-    case ABFT_MODE_SED: launch_spmv_mode<ABFT_MODE_SED>(c, m, x, y, red, active); break;
-    case ABFT_MODE_SEC7: launch_spmv_mode<ABFT_MODE_SEC7>(c, m, x, y, red, active); break;
-    case ABFT_MODE_SEC8: launch_spmv_mode<ABFT_MODE_SEC8>(c, m, x, y, red, active); break;
-    case ABFT_MODE_SECDED: launch_spmv_mode<ABFT_MODE_SECDED>(c, m, x, y, red, active); break;
-    case ABFT_MODE_CRC32C: launch_spmv_mode<ABFT_MODE_CRC32C>(c, m, x, y, red, active); break;
+    case ABFT_MODE_NONE: launch_spmv_mode<ABFT_MODE_NONE>(c, m, x, y, red, active, wait); break;
+    case ABFT_MODE_CONSTRAINTS: launch_spmv_mode<ABFT_MODE_CONSTRAINTS>(c, m, x, y, red, active, wait); break;
+    case ABFT_MODE_SED: launch_spmv_mode<ABFT_MODE_SED>(c, m, x, y, red, active, wait); break;
+    case ABFT_MODE_SEC7: launch_spmv_mode<ABFT_MODE_SEC7>(c, m, x, y, red, active, wait); break;
+    case ABFT_MODE_SEC8: launch_spmv_mode<ABFT_MODE_SEC8>(c, m, x, y, red, active, wait); break;
+    case ABFT_MODE_SECDED: launch_spmv_mode<ABFT_MODE_SECDED>(c, m, x, y, red, active, wait); break;
+    case ABFT_MODE_CRC32C: launch_spmv_mode<ABFT_MODE_CRC32C>(c, m, x, y, red, active, wait); break;
     default: return fail(-1, "bad mode", __FILE__, __LINE__);
   }
   c->launches++;
@@ -721,6 +740,209 @@ int abft_cuda_poll_events(abft_ctx *c, abft_event *out, int cap, int *fatal) {
     }
   }
   return n;
+}
+
+
+// ---------------------------------------------------------------------------
+// multi-GPU: peer-memory exchange over NVLink
+// ---------------------------------------------------------------------------
+abft_comm *abft_cuda_comm_create(abft_ctx *c, int rank, int world) {
+  if (!c || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) {
+    fail(-1, "bad arguments to comm_create (1..8 ranks)", __FILE__, __LINE__);
+    return nullptr;
+  }
+  CKP(cudaSetDevice(c->device));
+  abft_comm *m = new abft_comm();
+  m->rank = rank;
+  m->world = world;
+  CKP(cudaMalloc(&m->win[rank], sizeof(CommWindow)));
+  CKP(cudaMemset(m->win[rank], 0, sizeof(CommWindow)));
+  CKP(cudaDeviceSynchronize());
+  return m;
+}
+
+void abft_cuda_comm_destroy(abft_ctx *c, abft_comm *m) {
+  if (!m) return;
+  if (c) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+  }
+  for (int i = 0; i < m->n_ipc; i++) cudaIpcCloseMemHandle(m->ipc_opened[i]);
+  cudaFree(m->win[m->rank]);
+  delete m;
+}
+
+int abft_cuda_comm_window_handle(abft_ctx *c, abft_comm *m, unsigned char *out64) {
+  REQUIRE(c && m && out64, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == ABFT_IPC_HANDLE_BYTES, "IPC handle size");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, m->win[m->rank]));
+  memcpy(out64, &h, sizeof h);
+  return 0;
+}
+
+void *abft_cuda_comm_window_ptr(abft_comm *m) { return m ? (void *)m->win[m->rank] : nullptr; }
+
+int abft_cuda_vector_ipc_handle(abft_ctx *c, abft_vector *v, unsigned char *out64) {
+  REQUIRE(c && v && out64, "null argument");
+  REQUIRE(v->owns, "only vectors created by abft_cuda_vector_create can be exported");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, v->d));
+  memcpy(out64, &h, sizeof h);
+  return 0;
+}
+
+int abft_cuda_comm_attach_self(abft_ctx *c, abft_comm *m, abft_vector *vec_full) {
+  REQUIRE(c && m && vec_full, "null argument");
+  m->peer_vec[m->rank] = vec_full->d;
+  return 0;
+}
+
+int abft_cuda_comm_attach_peer(abft_ctx *c, abft_comm *m, int peer, const unsigned char *win_handle64,
+                               const unsigned char *vec_handle64) {
+  REQUIRE(c && m && win_handle64 && vec_handle64, "null argument");
+  REQUIRE(peer >= 0 && peer < m->world && peer != m->rank, "bad peer rank");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t hw, hv;
+  memcpy(&hw, win_handle64, sizeof hw);
+  memcpy(&hv, vec_handle64, sizeof hv);
+  void *pw = nullptr, *pv = nullptr;
+  CK(cudaIpcOpenMemHandle(&pw, hw, cudaIpcMemLazyEnablePeerAccess));
+  m->ipc_opened[m->n_ipc++] = pw;
+  CK(cudaIpcOpenMemHandle(&pv, hv, cudaIpcMemLazyEnablePeerAccess));
+  m->ipc_opened[m->n_ipc++] = pv;
+  m->win[peer] = (CommWindow *)pw;
+  m->peer_vec[peer] = (double *)pv;
+  return 0;
+}
+
+int abft_cuda_comm_attach_peer_ptrs(abft_ctx *c, abft_comm *m, int peer, void *window_dev, double *vec_dev,
+                                    int peer_device) {
+  REQUIRE(c && m && window_dev && vec_dev, "null argument");
+  REQUIRE(peer >= 0 && peer < m->world && peer != m->rank, "bad peer rank");
+  CK(cudaSetDevice(c->device));
+  if (peer_device != c->device) {
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    cudaGetLastError();
+  }
+  m->win[peer] = (CommWindow *)window_dev;
+  m->peer_vec[peer] = vec_dev;
+  return 0;
+}
+
+int abft_cuda_comm_set_plan(abft_ctx *c, abft_comm *m, const int *push_lo, const int *push_hi, unsigned int wait_mask,
+                            int row0) {
+  REQUIRE(c && m && push_lo && push_hi, "null argument");
+  for (int s = 0; s < m->world; s++) {
+    m->push_lo[s] = push_lo[s];
+    m->push_hi[s] = push_hi[s];
+  }
+  m->wait_mask = wait_mask & ~(1u << m->rank);
+  m->row0 = row0;
+  return 0;
+}
+
+}  // extern "C"
+
+static int comm_ready(abft_comm *m) {
+  for (int s = 0; s < m->world; s++)
+    if (!m->win[s] || !m->peer_vec[s]) return 0;
+  return 1;
+}
+
+template <bool COMPUTE>
+static int launch_push(abft_ctx *c, abft_comm *m, abft_vector *p_local, const abft_vector *r, double beta) {
+  REQUIRE(comm_ready(m), "comm: a peer has not been attached");
+  REQUIRE(p_local->d >= m->peer_vec[m->rank], "dist: p_local must be a view of the exchange vector");
+  REQUIRE((p_local->d - m->peer_vec[m->rank]) == m->row0, "dist: p_local must start at this rank's first row");
+  PushPlan plan{};
+  for (int s = 0; s < m->world; s++) {
+    plan.peer_vec[s] = m->peer_vec[s];
+    plan.win[s] = m->win[s];
+    plan.lo[s] = m->push_lo[s];
+    plan.hi[s] = m->push_hi[s];
+  }
+  plan.world = m->world;
+  plan.rank = m->rank;
+  plan.row0 = m->row0;
+  plan.epoch = ++m->epoch;
+  ScalarArg b{beta, nullptr, nullptr};
+  const int N = p_local->N;
+  long long want = ((long long)N + kBlock * 8 - 1) / (kBlock * 8);
+  const int grid = (int)std::max(1LL, std::min(want, (long long)c->num_sms * 8));
+  calc_p_push_kernel<false, COMPUTE><<<grid, kBlock, 0, c->stream>>>(p_local->d, COMPUTE ? r->d : p_local->d, b, N, plan,
+                                                                     nullptr);
+  c->launches++;
+  c->epoch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int abft_cuda_dist_push(abft_ctx *c, abft_comm *m, abft_vector *p_local) {
+  REQUIRE(c && m && p_local, "null argument");
+  CK(cudaSetDevice(c->device));
+  return launch_push<false>(c, m, p_local, nullptr, 0.0);
+}
+
+int abft_cuda_dist_calc_p(abft_ctx *c, abft_comm *m, abft_vector *p_local, const abft_vector *r, double beta) {
+  REQUIRE(c && m && p_local && r, "null argument");
+  REQUIRE(r->N >= p_local->N, "calc_p: vector lengths");
+  CK(cudaSetDevice(c->device));
+  return launch_push<true>(c, m, p_local, r, beta);
+}
+
+int abft_cuda_dist_spmv(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_vector *vec_full, abft_vector *result) {
+  REQUIRE(c && m && A && vec_full && result, "null argument");
+  REQUIRE(comm_ready(m), "comm: a peer has not been attached");
+  REQUIRE(vec_full->d == m->peer_vec[m->rank], "dist_spmv: vec must be the exchange vector");
+  REQUIRE((uint32_t)result->N >= A->view.n_rows && (uint32_t)vec_full->N >= A->view.n_cols, "dist_spmv: vector lengths");
+  CK(cudaSetDevice(c->device));
+  WaitSpec w{m->win[m->rank], m->epoch, m->wait_mask};
+  int rc = launch_spmv(c, A, vec_full->d, result->d, make_reduce(c, SLOT_SPMV_DOT, m), nullptr, w);
+  if (rc) return rc;
+  c->epoch++;
+  c->dot_a = vec_full->d + A->view.row_offset;
+  c->dot_b = result->d;
+  c->dot_n = (int)A->view.n_rows;
+  c->dot_epoch = c->epoch;
+  return 0;
+}
+
+int abft_cuda_dist_dot(abft_ctx *c, abft_comm *m, const abft_vector *a, const abft_vector *b, double *out) {
+  REQUIRE(c && m && a && b && out, "null argument");
+  CK(cudaSetDevice(c->device));
+  int slot = SLOT_DOT;
+  const bool fused = c->dot_epoch == c->epoch && a->N == c->dot_n && b->N >= a->N &&
+                     ((a->d == c->dot_a && b->d == c->dot_b) || (a->d == c->dot_b && b->d == c->dot_a));
+  if (fused) {
+    slot = SLOT_SPMV_DOT;  // dist_spmv already reduced it over all ranks
+  } else {
+    REQUIRE(b->N >= a->N, "dot: second vector shorter than the first");
+    int rc = launch_dot(c, a->d, b->d, a->N, make_reduce(c, SLOT_DOT, m), nullptr);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c->h_scalars[slot];
+  return 0;
+}
+
+int abft_cuda_dist_calc_xr(abft_ctx *c, abft_comm *m, abft_vector *x, abft_vector *r, const abft_vector *p,
+                           const abft_vector *w, double alpha, double *out) {
+  REQUIRE(c && m && x && r && p && w && out, "null argument");
+  REQUIRE(r->N >= x->N && p->N >= x->N && w->N >= x->N, "calc_xr: vector lengths");
+  CK(cudaSetDevice(c->device));
+  ScalarArg a{alpha, nullptr, nullptr};
+  int rc = launch_calc_xr(c, x->d, r->d, p->d, w->d, a, false, x->N, make_reduce(c, SLOT_XR, m), nullptr);
+  c->epoch++;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c->h_scalars[SLOT_XR];
+  return 0;
 }
 
 // ---------------------------------------------------------------------------

@@ -66,6 +66,53 @@ __device__ __forceinline__ double block_sum(double v, double *s_warp /* [kBlock/
   return t;
 }
 
+// ---- multi-GPU exchange window (one per rank, device memory, mapped into every peer) -------
+// Ranks PUSH into each other's windows / vectors with plain stores over NVLink (peer memory via
+// CUDA IPC or same-process peer access) and only ever READ their own memory.
+constexpr int kMaxRanks = 8;
+
+struct CommWindow {
+  double slots[2][kMaxRanks];      // [parity of the reduction sequence number][source rank]
+  unsigned int rflag[kMaxRanks];   // last reduction sequence number published by each source rank
+  unsigned int pflag[kMaxRanks];   // last vector-push epoch completed by each source rank
+  unsigned int push_counter;       // local: CTAs of the running push kernel that are done
+  unsigned int pad[15];
+};
+
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
+  return *reinterpret_cast<const volatile unsigned int *>(p);
+}
+__device__ __forceinline__ double ld_volatile_f64(const double *p) {
+  return *reinterpret_cast<const volatile double *>(p);
+}
+
+// Cross-rank part of a reduction: all-reduce (sum, fixed rank order => every rank gets the same
+// bits) of one double per rank through the peers' windows.  world == 0 or 1: local only.
+struct PeerReduce {
+  CommWindow *win[kMaxRanks];  // win[rank] is local
+  int world;
+  int rank;
+  unsigned int seq;            // this reduction's sequence number (same on every rank)
+};
+
+// called by ONE thread; returns the global sum
+__device__ __forceinline__ double peer_allreduce(double mine, const PeerReduce &pr) {
+  const int par = (int)(pr.seq & 1u);
+  for (int s = 0; s < pr.world; s++) pr.win[s]->slots[par][pr.rank] = mine;
+  __threadfence_system();
+  for (int s = 0; s < pr.world; s++) *reinterpret_cast<volatile unsigned int *>(&pr.win[s]->rflag[pr.rank]) = pr.seq;
+  const CommWindow *me = pr.win[pr.rank];
+  double total = 0.0;
+  for (int s = 0; s < pr.world; s++) {
+    // a rank can run at most one reduction ahead, and then it writes the other parity
+    while ((int)(ld_volatile_u32(&me->rflag[s]) - pr.seq) < 0) {
+    }
+  }
+  __threadfence_system();
+  for (int s = 0; s < pr.world; s++) total += ld_volatile_f64(&me->slots[par][s]);
+  return total;
+}
+
 // Where a reduction's final value goes and what the device-resident CG loop
 // derives from it (all optional).
 struct ReduceOut {
@@ -79,6 +126,7 @@ struct ReduceOut {
   double threshold;
   int max_itrs;
   int bump_iters;          // 1: this reduction closes an iteration (calc_xr)
+  PeerReduce peers;        // world > 1: the value published is the sum over all ranks
 };
 
 // Every CTA contributes `mine` (valid in thread 0); the CTA that arrives last
@@ -98,6 +146,7 @@ __device__ __forceinline__ void grid_sum_finalize(double mine, const ReduceOut &
   for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) acc += __ldcg(o.partials + i);
   double total = block_sum(acc, s_warp);
   if (threadIdx.x == 0) {
+    if (o.peers.world > 1) total = peer_allreduce(total, o.peers);
     *o.dev = total;
     if (o.host) *o.host = total;
     if (o.active) {

@@ -233,10 +233,17 @@ __device__ __forceinline__ uint32_t crc_word(uint32_t crc, uint32_t w, const uin
 
 __device__ uint32_t g_crc_tab[1024];  // filled by the host at library init
 
+// multi-GPU: the peers whose pushes into vec[] must have landed before it is read
+struct WaitSpec {
+  const CommWindow *me;  // local window
+  unsigned int epoch;    // wait until pflag[s] >= epoch ...
+  unsigned int mask;     // ... for every rank s in this mask (0: single GPU, no wait)
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, (MODE == ABFT_MODE_CRC32C) ? 3 : 4)
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
-            const int *__restrict__ active) {
+            const int *__restrict__ active, WaitSpec wait) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   StageBuf *stage = reinterpret_cast<StageBuf *>(dyn_smem);
   __shared__ __align__(8) uint64_t s_full[kStages];
@@ -288,6 +295,16 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
       issue((int)j, t);
     }
     if ((uint32_t)(kStages - 1) < n_my) ahead = A.tiles[blockIdx.x + (kStages - 1) * G];
+  }
+  if (wait.mask) {
+    // the matrix stream of the first tile is already in flight; vec[] is only touched after this
+    if (tid == 0) {
+      for (int s2 = 0; s2 < kMaxRanks; s2++)
+        if ((wait.mask >> s2) & 1u)
+          while ((int)(ld_volatile_u32(&wait.me->pflag[s2]) - wait.epoch) < 0) {
+          }
+      __threadfence_system();
+    }
   }
   __syncthreads();
 

@@ -110,4 +110,69 @@ calc_p_kernel(double *__restrict__ p, const double *__restrict__ r, ScalarArg be
     p[i] = __dadd_rn(r[i], __dmul_rn(beta, p[i]));
 }
 
+// ---- multi-GPU: p = r + beta p fused with the PUSH of the freshly computed entries into the
+// peers' copies of p over NVLink (plain stores to peer memory), then one flag per peer.
+// Which rows go where is the exchange plan built at setup from the partition's column
+// ranges: a banded matrix pushes a thin halo, an irregular one its whole slice (all-gather).
+struct PushPlan {
+  double *peer_vec[kMaxRanks];  // peers' full-length vectors, indexed by GLOBAL row
+  CommWindow *win[kMaxRanks];   // win[rank] is local
+  int lo[kMaxRanks], hi[kMaxRanks];  // global rows [lo, hi) of MY slice that peer s reads
+  int world, rank;
+  int row0;            // global row of local element 0
+  unsigned int epoch;  // published in the peers' pflag[rank] once every store has landed
+};
+
+template <bool DEV, bool COMPUTE>
+__global__ void __launch_bounds__(kBlock)
+calc_p_push_kernel(double *__restrict__ p, const double *__restrict__ r, ScalarArg beta_arg, int N, PushPlan plan,
+                   const int *__restrict__ active) {
+  if (active && *active == 0) return;
+  const double beta = COMPUTE ? scalar_of<DEV>(beta_arg) : 0.0;
+  constexpr int kPer = 8;
+  constexpr int kChunk = kBlock * kPer;
+  for (long long base = (long long)blockIdx.x * kChunk; base < N; base += (long long)gridDim.x * kChunk) {
+    double v[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; u++) {
+      const long long i = base + u * kBlock + threadIdx.x;
+      v[u] = 0.0;
+      if (i < N) {
+        if (COMPUTE) {
+          v[u] = __dadd_rn(r[i], __dmul_rn(beta, p[i]));
+          p[i] = v[u];
+        } else {
+          v[u] = p[i];
+        }
+      }
+    }
+    const long long g0 = plan.row0 + base;
+    const long long g1 = min(g0 + (long long)kChunk, (long long)plan.row0 + N);
+    for (int s = 0; s < plan.world; s++) {
+      const long long lo = max((long long)plan.lo[s], g0), hi = min((long long)plan.hi[s], g1);
+      if (s == plan.rank || lo >= hi) continue;  // uniform over the CTA
+      double *dst = plan.peer_vec[s];
+#pragma unroll
+      for (int u = 0; u < kPer; u++) {
+        const long long g = g0 + u * kBlock + threadIdx.x;
+        if (g >= lo && g < hi) dst[g] = v[u];
+      }
+    }
+  }
+  // completion: every thread fences its peer stores, the CTA that finishes last raises the flags
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    CommWindow *me = plan.win[plan.rank];
+    const unsigned int t = atomicAdd(&me->push_counter, 1u);
+    if (t == gridDim.x - 1) {
+      me->push_counter = 0u;
+      __threadfence_system();
+      for (int s = 0; s < plan.world; s++)
+        if (s != plan.rank && plan.hi[s] > plan.lo[s])
+          *reinterpret_cast<volatile unsigned int *>(&plan.win[s]->pflag[plan.rank]) = plan.epoch;
+    }
+  }
+}
+
 }  // namespace abft

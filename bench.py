@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--all-modes", type=int, default=1, help="also time every ABFT mode briefly (N=1 only)")
     ap.add_argument("--cpu-iters", type=int, default=5, help="iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = stores over NVLink fused into the kernels (product); nccl = all-gather/all-reduce calls (baseline)")
     return ap.parse_args()
 
 
@@ -214,14 +216,31 @@ def main():
         ctx.sync()
         return ctx, A, time.time() - tu
 
-    ctx, A, t_upload = setup(args.mode)
+    use_p2p = world > 1 and args.exchange == "p2p"
+    if use_p2p:
+        def all_gather_obj(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        ctx = pkg.CUDAContext(args.mode, local_rank)
+        tu = time.time()
+        cuts = [(N * k) // world for k in range(world + 1)]
+        dcg = pkg.dist.DistCG(ctx, rank, world, all_gather_obj, t, cuts, N, nnz_offset)
+        ctx.sync()
+        A, t_upload = dcg.A, time.time() - tu
+    else:
+        ctx, A, t_upload = setup(args.mode)
     stream = torch.cuda.ExternalStream(ctx.L.abft_cuda_ctx_stream(ctx.ctx), device=torch.device("cuda", local_rank))
 
     # vectors: p is full length on every rank (spmv gathers from it); the rest are the local slices
-    p_full_t = torch.zeros(N, dtype=torch.float64, device="cuda")
-    p_full = ctx.wrap_vector(p_full_t.data_ptr(), N)
-    p_loc = ctx.view_vector(p_full, r0, nloc)
-    vb, x, r, w = (ctx.create_vector(nloc) for _ in range(4))
+    if use_p2p:
+        p_full, p_loc, vb, x, r, w = dcg.p_full, dcg.p, dcg.b, dcg.x, dcg.r, dcg.w
+        p_full_t = None
+    else:
+        p_full_t = torch.zeros(N, dtype=torch.float64, device="cuda")
+        p_full = ctx.wrap_vector(p_full_t.data_ptr(), N)
+        p_loc = ctx.view_vector(p_full, r0, nloc)
+        vb, x, r, w = (ctx.create_vector(nloc) for _ in range(4))
     scal_t = torch.zeros(1, dtype=torch.float64, device="cuda")
 
     def allreduce(v):
@@ -247,12 +266,21 @@ def main():
     def start_solve():
         ctx.unmap_vector(vb, hb)          # H2D from the pinned map buffers
         ctx.unmap_vector(x, hx)
+        if use_p2p:
+            dcg.start()
+            state["rr"] = dcg.rr
+            return
         ctx.copy_vector(r, vb)
         ctx.copy_vector(p_loc, r)
         exchange_p()
         state["rr"] = allreduce(ctx.dot(r, r))
 
     def iterate(k):
+        if use_p2p:
+            dcg.rr = state["rr"]
+            dcg.iterate(k, 0.0)
+            state["rr"] = dcg.rr
+            return
         rr = state["rr"]
         for _ in range(k):
             ctx.spmv(A, p_full, w)
@@ -308,6 +336,7 @@ def main():
 
     # ---- roofline of the dominant kernel: spmv alone, back to back on the stream ----
     reps = max(20, min(args.steps, 100))
+    # (with the fused exchange the spmv alone would wait for a push that never comes: time the plain kernel)
     for _ in range(3):
         ctx.spmv(A, p_full, w)
     ms_spmv = timed(lambda: [ctx.spmv(A, p_full, w) for _ in range(reps)]) / reps
@@ -320,7 +349,11 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "rows_per_gpu": nloc, "nnz_per_gpu": nnz_local,
                        "partition": "1-D contiguous row blocks" if world > 1 else "single GPU",
-                       "exchange": "NCCL all-gather of p + all-reduce of 2 scalars" if world > 1 else "none",
+                       "exchange": ("none" if world == 1 else
+                                    "fused: halo of p stored into the peers' copies over NVLink inside calc_p, "
+                                    "scalars all-reduced through peer memory inside the reductions (%d B pushed per rank per iteration)"
+                                    % pkg.dist.exchanged_bytes(dcg.plan) if use_p2p else
+                                    "NCCL all-gather of p + all-reduce of 2 scalars (baseline)"),
                        "l2": "inputs larger than L2 (matrix stream %.0f MB per GPU per iteration)" % (12 * nnz_local / 1e6),
                        "abi": "C ABI of include/abft_cuda.h via ctypes (host scalars every iteration)"},
             "e2e": {"value": its_e2e, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -183,6 +183,44 @@ int abft_cuda_cg_solve(abft_ctx *ctx, abft_matrix *A, const abft_vector *b, abft
                        abft_vector *p, abft_vector *w, int max_itrs, double conv_threshold, int check_every,
                        double *rr_out);
 
+/* ---- multi-GPU: row-partitioned CG with the exchange fused into the kernels ----
+ * One context per GPU (one process per GPU, or several contexts in one process).  Every rank owns a
+ * row block of A (abft_cuda_matrix_create_part), the matching slices of x, r, w, b, and a FULL-length
+ * copy of the search direction p (the "exchange vector", created with abft_cuda_vector_create).
+ * Ranks never read remote memory: dist_calc_p computes p = r + beta p on its slice and, in the same
+ * kernel, STORES the entries its peers' rows reference straight into their copies of p over NVLink
+ * (peer memory: CUDA IPC between processes, peer access inside one), then raises one flag per peer;
+ * dist_spmv spins on those flags before it touches p.  The two scalars per iteration are all-reduced
+ * inside the reduction's last CTA the same way (each rank stores its partial into every peer's window
+ * and adds the G partials in rank order, so all ranks get identical bits; no NCCL call on the path).
+ * The plan (which rows each peer needs) comes from the partition's column ranges: a banded matrix
+ * exchanges a halo, an irregular one degenerates to an all-gather.
+ * All ranks must issue the same sequence of dist_* calls. */
+#define ABFT_IPC_HANDLE_BYTES 64
+typedef struct abft_comm abft_comm;
+abft_comm *abft_cuda_comm_create(abft_ctx *ctx, int rank, int world); /* world <= 8 */
+void abft_cuda_comm_destroy(abft_ctx *ctx, abft_comm *comm);
+/* handles to send to the peers (any transport; bench.py uses torch.distributed) */
+int abft_cuda_comm_window_handle(abft_ctx *ctx, abft_comm *comm, unsigned char *out64);
+int abft_cuda_vector_ipc_handle(abft_ctx *ctx, abft_vector *vec, unsigned char *out64);
+void *abft_cuda_comm_window_ptr(abft_comm *comm); /* same-process peers exchange raw pointers */
+int abft_cuda_comm_attach_self(abft_ctx *ctx, abft_comm *comm, abft_vector *vec_full);
+int abft_cuda_comm_attach_peer(abft_ctx *ctx, abft_comm *comm, int peer, const unsigned char *window_handle64,
+                               const unsigned char *vec_handle64);
+int abft_cuda_comm_attach_peer_ptrs(abft_ctx *ctx, abft_comm *comm, int peer, void *window_dev, double *vec_dev,
+                                    int peer_device);
+/* push_lo/hi[s]: GLOBAL rows [lo, hi) of this rank's slice that rank s reads (lo >= hi: none);
+ * wait_mask: bit s set if rank s pushes to this rank; row0: this rank's first global row */
+int abft_cuda_comm_set_plan(abft_ctx *ctx, abft_comm *comm, const int *push_lo, const int *push_hi,
+                            unsigned int wait_mask, int row0);
+int abft_cuda_dist_push(abft_ctx *ctx, abft_comm *comm, abft_vector *p_local); /* initial p = r exchange */
+int abft_cuda_dist_calc_p(abft_ctx *ctx, abft_comm *comm, abft_vector *p_local, const abft_vector *r, double beta);
+int abft_cuda_dist_spmv(abft_ctx *ctx, abft_comm *comm, abft_matrix *mat, const abft_vector *vec_full,
+                        abft_vector *result);
+int abft_cuda_dist_dot(abft_ctx *ctx, abft_comm *comm, const abft_vector *a, const abft_vector *b, double *out);
+int abft_cuda_dist_calc_xr(abft_ctx *ctx, abft_comm *comm, abft_vector *x, abft_vector *r, const abft_vector *p,
+                           const abft_vector *w, double alpha, double *out);
+
 /* ---- introspection for bench.py / tests ---- */
 /* number of kernels this library has launched on the context since creation */
 uint64_t abft_cuda_launch_count(const abft_ctx *ctx);
