@@ -57,7 +57,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -76,7 +76,9 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary over the samples taken in [t_begin, t_end] (time.time() values; None = all)."""
+        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -86,20 +88,25 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        total = 0
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
+            total += 1
             try:
-                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.05):
+                    continue
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        busy = [s for s, p in zip(sm, power) if p > 300.0] or sm
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples_in_timed_region": len(sm),
+                "samples_total": total, "reasons": sorted(reasons)}
 
 
 def slab_triplets(mg, grid, r0, r1):
@@ -186,12 +193,14 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout and would precede the JSON line
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi takes a while to spin up
     # row partition (contiguous, balanced by rows == by nnz up to the boundary planes)
     r0 = (N * rank) // world
     r1 = (N * (rank + 1)) // world
@@ -315,12 +324,13 @@ def main():
 
     # ---- value: K iterations, operands resident in HBM ----
     start_solve()
-    sampler = ClockSampler(local_rank) if rank == 0 else None   # sampled from the warm-up on: the timed region is short
     iterate(max(args.warmup, 3))
     l0 = ctx.launch_count()
+    t_begin = time.time()
     ms_total = timed(lambda: iterate(args.steps))
+    t_end = time.time()
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
     its = args.steps / (ms_total * 1e-3)
     ctx.report_faults()
 

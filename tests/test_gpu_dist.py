@@ -45,9 +45,9 @@ def test_dist_fault_reports_global_index(pkg, O, tmp_path):
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     res = run_worker(world, "gpu", "p2d", tmp_path, extra=["secded", "flip"])
-    gi = res["e0_last"] + 7
+    t = pkg.matgen.poisson2d(24)
+    gi = int(t.row_pointers()[res["cuts"][-2]]) + 7      # element 7 of the LAST rank's block, as a global index
     assert res["lines"][-1] == [f"[ECC] corrected bit 33 at index {gi}"]
     assert all(lines == [] for lines in res["lines"][:-1])
-    t = pkg.matgen.poisson2d(24)
     ref = O.OracleMatrix("secded", t.cols, t.rows, t.vals, t.N).cg(pkg.matgen.rhs(t.N), 2000, 1e-10)
     assert all(r["iterations"] == ref["iterations"] for r in res["all"])
