@@ -154,8 +154,21 @@ def cpu_reference_run(args, t, b, iters, warm):
     return done / dt, dt, t_create, kind
 
 
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else written to fd 1 meanwhile (NCCL's version
+    banner, library chatter) was diverted to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,7 +202,7 @@ def main():
                 "cpu_baseline": {"value": its, "unit": "it/s", "cores": cores, "kind": kind,
                                  "sample": f"{args.steps} CG iterations on the full matrix after {args.warmup} warm-up"},
                 "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -440,7 +453,7 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "unavailable",
                                         "sample": str(e)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
