@@ -10,7 +10,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libabftcuda.so")
+LIB_PATH = os.environ.get("ABFT_CUDA_LIB") or os.path.join(HERE, "libabftcuda.so")   # override: kernel experiments
 
 MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"]
 FATAL_KINDS = {1, 4, 5, 6, 7, 8, 9}

@@ -34,6 +34,7 @@ namespace abft {
 constexpr int kTileNnz = 2048;
 constexpr int kTileRows = kBlock;  // 256: one row per thread
 constexpr int kStages = 2;
+constexpr uint32_t kOverrun = 8;  // elements staged past a tile's end (>= longest unrolled walk - 1)
 
 constexpr uint32_t kTileRegular = 1u << 16;  // info flag: thread-per-row path
 constexpr uint32_t kTileLongRow = 1u << 17;  // info flag: single row > kTileNnz, streamed
@@ -59,9 +60,11 @@ struct MatView {
 };
 
 // one pipeline stage of staged tile data (windows start at 16-byte aligned indices)
+// (+16: the windows are rounded out to 16 bytes, and the unrolled row walk may read up to 6 slots
+// past a row's end)
 struct __align__(16) StageBuf {
-  double vals[kTileNnz + 2];
-  uint32_t cols[kTileNnz + 8];
+  double vals[kTileNnz + 16];
+  uint32_t cols[kTileNnz + 16];
   uint32_t rptr[kTileRows + 8];
 };
 constexpr size_t kSpmvDynSmem = sizeof(StageBuf) * kStages;
@@ -160,6 +163,20 @@ __device__ __forceinline__ uint32_t element_suspect_bits(uint32_t w0, uint32_t w
   return 0;
 }
 
+// acc | (verdict bits of one element), written as a flat chain of 3-input ORs (one LOP3 each)
+template <int MODE>
+__device__ __forceinline__ uint32_t or_suspect_bits(uint32_t acc, uint32_t w0, uint32_t w1, uint32_t col) {
+  if (MODE == ABFT_MODE_SED || MODE == ABFT_MODE_SEC8) return acc | __popc(w0 ^ w1 ^ col);
+  if (MODE == ABFT_MODE_SEC7 || MODE == ABFT_MODE_SECDED) {
+    acc = acc | __popc(masked<1>(w0, w1, col)) | __popc(masked<2>(w0, w1, col));
+    acc = acc | __popc(masked<3>(w0, w1, col)) | __popc(masked<4>(w0, w1, col));
+    acc = acc | __popc(masked<5>(w0, w1, col)) | __popc(masked<6>(w0, w1, col));
+    if (MODE == ABFT_MODE_SECDED) acc = acc | __popc(masked<7>(w0, w1, col)) | __popc(w0 ^ w1 ^ col);
+    else acc = acc | __popc(masked<7>(w0, w1, col));
+  }
+  return acc;
+}
+
 template <int MODE>
 struct ModeTraits {
   static constexpr bool per_element_ecc = MODE >= ABFT_MODE_SED && MODE <= ABFT_MODE_SECDED;
@@ -193,34 +210,39 @@ __device__ __forceinline__ double element_product(uint32_t cw, double v, uint32_
 // loads first, then all checks and gathers (LEN independent loads in flight), then the products
 // are added to `sum` in element order.  No per-element branch: the checks only OR their verdict
 // into `suspect`; the caller re-walks the row on the careful path if bit 0 ends up set (rare).
+// Slots past the row's end (k >= count) are still loaded and checked -- they hold the next row's
+// elements, stale elements of an earlier tile, or the zeros the buffers start with, i.e. valid code
+// words (the stage is filled kOverrun elements past the tile's end for exactly this), and at worst
+// a false `suspect` sends the row down the (exact) careful path -- but they are never added.  That
+// keeps the loop body free of selects and zero-fills.
 template <int MODE, int LEN>
 __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_t count, const uint32_t *s_cols,
                                              const double *s_vals, uint32_t n_cols, const double *__restrict__ x,
                                              uint32_t &suspect) {
   uint32_t c[LEN];
   double v[LEN], xv[LEN];
+  bool ok[LEN];
 #pragma unroll
   for (int k = 0; k < LEN; k++) {
-    c[k] = 0;   // an absent element reads as {+0.0, column 0}: a valid code word in every mode
-    v[k] = 0.0;
-    if ((uint32_t)k < count) {
-      c[k] = s_cols[first + k];
-      v[k] = s_vals[first + k];
-    }
+    c[k] = s_cols[first + k];
+    v[k] = s_vals[first + k];
   }
 #pragma unroll
   for (int k = 0; k < LEN; k++) {
     if (ModeTraits<MODE>::per_element_ecc) {
       uint32_t w0, w1;
       split_value(v[k], w0, w1);
-      suspect |= element_suspect_bits<MODE>(w0, w1, c[k]);
+      suspect = or_suspect_bits<MODE>(suspect, w0, w1, c[k]);
     }
     const uint32_t col = ModeTraits<MODE>::masks_column ? (c[k] & 0x00FFFFFFu) : c[k];
-    xv[k] = (col < n_cols) ? __ldg(x + col) : 0.0;
+    // a column no check caught can point outside vec[] (the reference reads out of bounds: UB; here
+    // the element contributes nothing): gather from a clamped address, drop the product below
+    ok[k] = ((uint32_t)k < count) && (col < n_cols);
+    xv[k] = __ldg(x + min(col, n_cols - 1u));
   }
 #pragma unroll
   for (int k = 0; k < LEN; k++)
-    if ((uint32_t)k < count) sum = __dadd_rn(sum, __dmul_rn(v[k], xv[k]));
+    if (ok[k]) sum = __dadd_rn(sum, __dmul_rn(v[k], xv[k]));
   return sum;
 }
 
@@ -240,8 +262,12 @@ struct WaitSpec {
   unsigned int mask;     // ... for every rank s in this mask (0: single GPU, no wait)
 };
 
+#ifndef ABFT_SPMV_MINB
+#define ABFT_SPMV_MINB 4  // resident CTAs per SM the register allocation is tuned for
+#endif
+
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, (MODE == ABFT_MODE_CRC32C) ? 3 : 4)
+__global__ void __launch_bounds__(kBlock, (MODE == ABFT_MODE_CRC32C) ? 3 : ABFT_SPMV_MINB)
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
             const int *__restrict__ active, WaitSpec wait) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -257,11 +283,18 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   const uint32_t G = gridDim.x;
   const uint32_t n_my = (A.n_tiles > blockIdx.x) ? (A.n_tiles - blockIdx.x + G - 1) / G : 0;
 
+  {
+    // the row walk may look a few slots past the data TMA delivers: start from all-zero buffers
+    // (a zero element is a valid code word in every mode)
+    uint4 *z = reinterpret_cast<uint4 *>(dyn_smem);
+    for (uint32_t i = tid; i < kSpmvDynSmem / 16; i += kBlock) z[i] = make_uint4(0, 0, 0, 0);
+  }
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&s_full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  __syncthreads();
+  if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (MODE == ABFT_MODE_CRC32C)
     for (int i = tid; i < 1024; i += kBlock) s_crc[i] = g_crc_tab[i];
   __syncthreads();
@@ -274,9 +307,11 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     const uint32_t rbytes = ((t.row_begin + nrows + 1 + 3) & ~3u) * 4u - rb * 4u;
     uint32_t cbytes = 0, vbytes = 0;
     const uint32_t cb = t.nnz_begin & ~3u, vb = t.nnz_begin & ~1u;
-    if (!(t.info & kTileLongRow) && t.nnz_end > t.nnz_begin) {
-      cbytes = ((t.nnz_end + 3) & ~3u) * 4u - cb * 4u;
-      vbytes = ((t.nnz_end + 1) & ~1u) * 8u - vb * 8u;
+    if (!(t.info & kTileLongRow)) {
+      // kOverrun real elements past the tile's end come along: the unrolled row walk may look that far
+      // past a row's end, and must find matched (column, value) pairs there, not stale halves
+      cbytes = ((t.nnz_end + kOverrun + 3) & ~3u) * 4u - cb * 4u;
+      vbytes = ((t.nnz_end + kOverrun + 1) & ~1u) * 8u - vb * 8u;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&s_full[s], rbytes + cbytes + vbytes);
@@ -441,8 +476,8 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
             else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
             else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
             else
-              for (uint32_t base = 0; base < max_len; base += 8)
-                sum = walk_chunk<MODE, 8>(sum, base, len > base ? len - base : 0u, sc, sv, A.n_cols, x, suspect);
+              for (uint32_t base = 0; base < max_len; base += 4)
+                sum = walk_chunk<MODE, 4>(sum, base, len > base ? len - base : 0u, sc, sv, A.n_cols, x, suspect);
             if (suspect & 1u) {
               // a check tripped somewhere in this row: walk it again element by element, repairing /
               // reporting as the mode demands (the owning thread writes the element back)
