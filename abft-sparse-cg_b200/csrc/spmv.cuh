@@ -219,7 +219,7 @@ template <int MODE, int LEN>
 __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_t count, const uint32_t *s_cols,
                                              const double *s_vals, uint32_t n_cols, const double *__restrict__ x,
                                              uint32_t &suspect) {
-  uint32_t c[LEN];
+  uint32_t c[LEN + 1];
   double v[LEN], xv[LEN];
   bool ok[LEN];
 #pragma unroll
@@ -227,8 +227,14 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
     c[k] = s_cols[first + k];
     v[k] = s_vals[first + k];
   }
+  if (MODE == ABFT_MODE_CONSTRAINTS) c[LEN] = s_cols[first + LEN];
 #pragma unroll
   for (int k = 0; k < LEN; k++) {
+    if (MODE == ABFT_MODE_CONSTRAINTS) {
+      // CSR/CPUContext.cpp:188-200: col < N, and strictly increasing inside the row
+      suspect |= (c[k] >= n_cols) ? 1u : 0u;
+      suspect |= ((uint32_t)(k + 1) < count && c[k + 1] <= c[k]) ? 1u : 0u;
+    }
     if (ModeTraits<MODE>::per_element_ecc) {
       uint32_t w0, w1;
       split_value(v[k], w0, w1);
@@ -415,33 +421,53 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
       }
       if (has_row) {
         uint32_t rs = B.rptr[row - rb], re = B.rptr[row + 1 - rb];
-        bool row_ok = true;
-        if (MODE == ABFT_MODE_CONSTRAINTS) {
-          // CSR/CPUContext.cpp:173-182
-          if (re > A.nnz) { log_event(L, ABFT_EV_ROW_SIZE, A.row_offset + row, 0); row_ok = false; }
-          else if (re < rs) { log_event(L, ABFT_EV_ROW_ORDER, A.row_offset + row, 0); row_ok = false; }
-        } else {
-          // other modes trust rows[] like the reference; clamp so a bad pointer cannot fault
+        double sum = 0.0;
+        bool careful = true;
+        if (MODE != ABFT_MODE_CONSTRAINTS) {
+          // these modes trust rows[] like the reference; clamp so a bad pointer cannot fault
           rs = min(max(rs, t.nnz_begin), t.nnz_end);
           re = min(max(re, rs), t.nnz_end);
         }
-        double sum = 0.0;
-        if (row_ok) {
+        // ---------------- regular tile: thread-per-row straight from the staged stream ----------------
+        // (CONSTRAINTS only if its row pointers keep the row inside the staged window; anything else,
+        // i.e. a corrupted rows[], takes the careful path that mirrors the reference's checks one by one)
+        if ((t.info & kTileRegular) && MODE != ABFT_MODE_CRC32C &&
+            (MODE != ABFT_MODE_CONSTRAINTS || (rs >= t.nnz_begin && re <= t.nnz_end && rs <= re))) {
+          const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the CTA
+          const uint32_t len = re - rs;
+          const uint32_t *sc = B.cols + (rs - cb);
+          const double *sv = B.vals + (rs - vb);
+          uint32_t suspect = 0;
+          if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
+          else if (max_len == 5) sum = walk_chunk<MODE, 5>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
+          else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
+          else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
+          else
+            for (uint32_t base = 0; base < max_len; base += 4)
+              sum = walk_chunk<MODE, 4>(sum, base, len > base ? len - base : 0u, sc, sv, A.n_cols, x, suspect);
+          careful = (suspect & 1u) != 0;  // a check tripped somewhere in this row: walk it again, carefully
+        }
+        if (careful) {
+          sum = 0.0;
           if (MODE == ABFT_MODE_CONSTRAINTS) {
-            for (uint32_t i = rs; i < re; i++) {
-              // elements normally sit in the staged window; a corrupted row pointer can send the
-              // row outside it, then go to global memory (i < nnz was checked above)
-              const bool in = (i >= t.nnz_begin) && (i < t.nnz_end);
-              const uint32_t col = in ? B.cols[i - cb] : A.cols[i];
-              if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + row); break; }
-              if (i < re - 1) {
-                const bool in2 = (i + 1 >= t.nnz_begin) && (i + 1 < t.nnz_end);
-                const uint32_t nxt = in2 ? B.cols[i + 1 - cb] : A.cols[i + 1];
-                if (nxt <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + row); break; }
+            // CSR/CPUContext.cpp:173-182, then :184-203
+            if (re > A.nnz) log_event(L, ABFT_EV_ROW_SIZE, A.row_offset + row, 0);
+            else if (re < rs) log_event(L, ABFT_EV_ROW_ORDER, A.row_offset + row, 0);
+            else
+              for (uint32_t i = rs; i < re; i++) {
+                // elements normally sit in the staged window; a corrupted row pointer can send the
+                // row outside it, then go to global memory (i < nnz was checked above)
+                const bool in = (i >= t.nnz_begin) && (i < t.nnz_end);
+                const uint32_t col = in ? B.cols[i - cb] : A.cols[i];
+                if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + row); break; }
+                if (i < re - 1) {
+                  const bool in2 = (i + 1 >= t.nnz_begin) && (i + 1 < t.nnz_end);
+                  const uint32_t nxt = in2 ? B.cols[i + 1 - cb] : A.cols[i + 1];
+                  if (nxt <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + row); break; }
+                }
+                const double val = in ? B.vals[i - vb] : A.values[i];
+                sum = __dadd_rn(sum, __dmul_rn(val, __ldg(x + col)));
               }
-              const double val = in ? B.vals[i - vb] : A.values[i];
-              sum = __dadd_rn(sum, __dmul_rn(val, __ldg(x + col)));
-            }
           } else if (MODE == ABFT_MODE_CRC32C) {
             const uint32_t len = re - rs;
             uint32_t crc = 0xFFFFFFFFu, stored = 0;
@@ -465,26 +491,10 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
             if (len >= 4 && (crc ^ 0xFFFFFFFFu) != stored) bad = true;
             if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
           } else if (t.info & kTileRegular) {
-            // ---------------- regular tile: thread-per-row straight from the staged stream ----------------
-            const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the CTA
-            const uint32_t len = re - rs;
-            const uint32_t *sc = B.cols + (rs - cb);
-            const double *sv = B.vals + (rs - vb);
-            uint32_t suspect = 0;
-            if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
-            else if (max_len == 5) sum = walk_chunk<MODE, 5>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
-            else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
-            else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
-            else
-              for (uint32_t base = 0; base < max_len; base += 4)
-                sum = walk_chunk<MODE, 4>(sum, base, len > base ? len - base : 0u, sc, sv, A.n_cols, x, suspect);
-            if (suspect & 1u) {
-              // a check tripped somewhere in this row: walk it again element by element, repairing /
-              // reporting as the mode demands (the owning thread writes the element back)
-              sum = 0.0;
-              for (uint32_t i = rs; i < re; i++)
-                sum = __dadd_rn(sum, element_product<MODE>(B.cols[i - cb], B.vals[i - vb], i, A, x, L));
-            }
+            // element by element, repairing / reporting as the mode demands (the owning thread
+            // writes a corrected element back)
+            for (uint32_t i = rs; i < re; i++)
+              sum = __dadd_rn(sum, element_product<MODE>(B.cols[i - cb], B.vals[i - vb], i, A, x, L));
           } else {
             // ---------------- irregular tile, row phase: add the products in element order ----------------
 #pragma unroll 4

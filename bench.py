@@ -38,6 +38,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--mode", default="secded")
     ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--workload", default="poisson3d", choices=["poisson3d", "poisson2d_blocks", "powerlaw"],
+                    help="poisson3d: grid^3 7-point (default, BASELINE configs[2]); poisson2d_blocks: 512^2 5-point x 64 "
+                         "diagonal blocks (largest 5-point case the 24-bit column allows, configs[3]); powerlaw: irregular "
+                         "rows, N=2^21, ~5e7 nnz (configs[4], scaled)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--all-modes", type=int, default=1, help="also time every ABFT mode briefly (N=1 only)")
     ap.add_argument("--cpu-iters", type=int, default=5, help="iterations of the CPU baseline sample")
@@ -179,17 +183,25 @@ def main():
     pkg = pkg_loader.load()
     mg = pkg.matgen
     n = args.grid
-    N = n ** 3
-    nnz = 7 * N - 6 * n * n
+    full = None
+    if args.workload == "poisson3d":
+        N = n ** 3
+        nnz = 7 * N - 6 * n * n
+        workload = f"poisson3d_{n} (3D 7-point Poisson {n}^3: N={N}, nnz={nnz}), mode {args.mode}, -c 0 -i K"
+    else:
+        full = mg.poisson2d(512, 64) if args.workload == "poisson2d_blocks" else mg.powerlaw(1 << 21, 50_000_000, seed=1)
+        N, nnz = full.N, full.nnz
+        what = ("2D 5-point Poisson 512^2 replicated -b 64" if args.workload == "poisson2d_blocks"
+                else "power-law row lengths (Zipf 2.0, <= 4096 per row), SPD")
+        workload = f"{args.workload} ({what}: N={N}, nnz={nnz}), mode {args.mode}, -c 0 -i K"
     B_alg, B_spmv = alg_bytes(N, nnz)
     peak, peak_src = peaks()
-    workload = f"poisson3d_{n} (3D 7-point Poisson {n}^3: N={N}, nnz={nnz}), mode {args.mode}, -c 0 -i K"
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
-        t = slab_triplets(mg, n, 0, N)
+        t = slab_triplets(mg, n, 0, N) if full is None else full
         b = np.random.default_rng(1).random(N)
         its, dt, t_create, kind = cpu_reference_run(args, t, b, args.steps, args.warmup)
         cores = os.cpu_count()
@@ -215,10 +227,17 @@ def main():
 
     sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi takes a while to spin up
     # row partition (contiguous, balanced by rows == by nnz up to the boundary planes)
-    r0 = (N * rank) // world
-    r1 = (N * (rank + 1)) // world
     t_gen = time.time()
-    t = slab_triplets(mg, n, r0, r1)
+    if full is None:
+        cuts = [(N * k) // world for k in range(world + 1)]
+        r0, r1 = cuts[rank], cuts[rank + 1]
+        t = slab_triplets(mg, n, r0, r1)
+    else:
+        rowptr = full.row_pointers().astype(np.int64)
+        cuts = pkg.dist.balanced_row_cuts(rowptr, world)
+        r0, r1 = cuts[rank], cuts[rank + 1]
+        e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+        t = mg.Triplets(full.cols[e0:e1], full.rows[e0:e1], full.vals[e0:e1], N)
     t_gen = time.time() - t_gen
     nnz_local = t.nnz
     if world > 1:
@@ -246,7 +265,6 @@ def main():
             return out
         ctx = pkg.CUDAContext(args.mode, local_rank)
         tu = time.time()
-        cuts = [(N * k) // world for k in range(world + 1)]
         dcg = pkg.dist.DistCG(ctx, rank, world, all_gather_obj, t, cuts, N, nnz_offset)
         ctx.sync()
         A, t_upload = dcg.A, time.time() - tu
