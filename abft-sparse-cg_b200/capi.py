@@ -34,7 +34,7 @@ SYMBOLS = [
     "abft_cuda_comm_create", "abft_cuda_comm_destroy", "abft_cuda_comm_window_handle", "abft_cuda_vector_ipc_handle",
     "abft_cuda_comm_window_ptr", "abft_cuda_comm_attach_self", "abft_cuda_comm_attach_peer",
     "abft_cuda_comm_attach_peer_ptrs", "abft_cuda_comm_set_plan", "abft_cuda_dist_push", "abft_cuda_dist_calc_p",
-    "abft_cuda_dist_spmv", "abft_cuda_dist_dot", "abft_cuda_dist_calc_xr",
+    "abft_cuda_dist_spmv", "abft_cuda_dist_dot", "abft_cuda_dist_calc_xr", "abft_cuda_dist_cg_solve",
 ]
 
 
@@ -125,6 +125,7 @@ def load():
     sig("abft_cuda_dist_spmv", i32, vp, vp, vp, vp, vp)
     sig("abft_cuda_dist_dot", i32, vp, vp, vp, vp, f64p)
     sig("abft_cuda_dist_calc_xr", i32, vp, vp, vp, vp, vp, vp, f64, f64p)
+    sig("abft_cuda_dist_cg_solve", i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, i32, f64p)
     _lib = L
     return L
 

@@ -948,6 +948,132 @@ int abft_cuda_dist_calc_xr(abft_ctx *c, abft_comm *m, abft_vector *x, abft_vecto
 // ---------------------------------------------------------------------------
 // device-resident CG loop
 // ---------------------------------------------------------------------------
+}  // extern "C"
+
+// One implementation for the single-GPU and the row-partitioned loop.  comm == nullptr: p_full == p_local.
+static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_vector *b, abft_vector *x, abft_vector *r,
+                         abft_vector *p_local, abft_vector *p_full, abft_vector *w, int max_itrs, double conv_threshold,
+                         int check_every, double *rr_out) {
+  const int N = (int)A->view.n_rows;
+  if (check_every < 1) check_every = 1;
+  if (cudaSetDevice(c->device) != cudaSuccess) return -1;
+  cudaStream_t s = c->stream;
+  int *flag0 = c->d_loop, *iters = c->d_loop + 2;
+  cudaMemsetAsync(c->d_loop, 0, sizeof(int) * 4, s);
+  c->h_loop[0] = 0;
+  c->h_loop[1] = 0;
+  const unsigned int seq0 = m ? m->seq : 0u, epoch0 = m ? m->epoch : 0u;
+
+  auto push_plan = [&](PushPlan &plan) {
+    for (int k = 0; k < m->world; k++) {
+      plan.peer_vec[k] = m->peer_vec[k];
+      plan.win[k] = m->win[k];
+      plan.lo[k] = m->push_lo[k];
+      plan.hi[k] = m->push_hi[k];
+    }
+    plan.world = m->world;
+    plan.rank = m->rank;
+    plan.row0 = m->row0;
+    plan.epoch = ++m->epoch;
+  };
+  const long long want = ((long long)N + kBlock * 8 - 1) / (kBlock * 8);
+  const int push_grid = (int)std::max(1LL, std::min(want, (long long)c->num_sms * 8));
+
+  // r = b ; p = r (+ exchange) ; rr = r.r   (cg.cpp:87-91)
+  cudaMemcpyAsync(r->d, b->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s);
+  cudaMemcpyAsync(p_local->d, r->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s);
+  if (m) {
+    PushPlan plan{};
+    push_plan(plan);
+    ScalarArg none{0.0, nullptr, nullptr};
+    calc_p_push_kernel<false, false><<<push_grid, kBlock, 0, s>>>(p_local->d, p_local->d, none, N, plan, nullptr);
+    c->launches++;
+  }
+  {
+    ReduceOut red = make_reduce(c, SLOT_RR0, m);
+    red.active = flag0;  // iteration 0 reads flag[0]
+    red.iters = iters;
+    red.threshold = conv_threshold;
+    red.max_itrs = max_itrs;
+    red.bump_iters = 0;
+    if (launch_dot(c, r->d, r->d, N, red, nullptr)) return -1;
+  }
+  c->epoch++;
+  int launched = 0;
+  int done_iters = 0;
+  bool active = true;
+  bool fatal_seen = false;
+  while (active && launched < max_itrs) {
+    const int batch = std::min(check_every, max_itrs - launched);
+    for (int j = 0; j < batch; j++, launched++) {
+      const int q = launched & 1;
+      const int *flag_cur = c->d_loop + q;
+      int *flag_next = c->d_loop + (q ^ 1);
+      const double *rr_cur = c->d_scalars + (q ? SLOT_RR1 : SLOT_RR0);
+      const int slot_new = q ? SLOT_RR0 : SLOT_RR1;
+      // w = A p, pw = p.w (summed over all ranks inside the kernel's finalizer)
+      WaitSpec wait{m ? m->win[m->rank] : nullptr, m ? m->epoch : 0u, m ? m->wait_mask : 0u};
+      if (launch_spmv(c, A, p_full->d, w->d, make_reduce(c, SLOT_SPMV_DOT, m), flag_cur, wait)) return -1;
+      // alpha = rr / pw ; x += alpha p ; r -= alpha w ; rr_new = r.r
+      ReduceOut red = make_reduce(c, slot_new, m);
+      red.active = flag_next;
+      red.iters = iters;
+      red.threshold = conv_threshold;
+      red.max_itrs = max_itrs;
+      red.bump_iters = 1;
+      ScalarArg alpha{0.0, rr_cur, c->d_scalars + SLOT_SPMV_DOT};
+      if (launch_calc_xr(c, x->d, r->d, p_local->d, w->d, alpha, true, N, red, flag_cur)) return -1;
+      // beta = rr_new / rr ; p = r + beta p (+ push of the new entries to the peers)
+      ScalarArg beta{0.0, c->d_scalars + slot_new, rr_cur};
+      if (m) {
+        PushPlan plan{};
+        push_plan(plan);
+        calc_p_push_kernel<true, true><<<push_grid, kBlock, 0, s>>>(p_local->d, r->d, beta, N, plan, flag_cur);
+        c->launches++;
+      } else if (launch_calc_p(c, p_local->d, r->d, beta, true, N, flag_cur)) {
+        return -1;
+      }
+    }
+    // read back progress: iterations done and whether the next one would run
+    cudaMemcpyAsync(c->h_loop, c->d_loop + 2, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(c->h_loop + 1, c->d_loop + (launched & 1), sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      fail(-1, "cg_solve: stream sync failed", __FILE__, __LINE__);
+      return -1;
+    }
+    done_iters = c->h_loop[0];
+    active = c->h_loop[1] != 0;
+    if (*c->h_flag) {
+      // a fault was logged; a fatal one stops the single-GPU solve like the reference's exit(1).  Ranks of a
+      // partitioned solve must keep issuing the same kernels (they wait on each other): they finish the loop
+      // and the caller finds the fault with abft_cuda_poll_events afterwards.
+      unsigned int count = 0;
+      cudaMemcpy(&count, &c->d_log->count, sizeof count, cudaMemcpyDeviceToHost);
+      count = std::min(count, (unsigned)kLogCap);
+      std::vector<abft_event> ev(count);
+      if (count) cudaMemcpy(ev.data(), c->d_log->ev, sizeof(abft_event) * count, cudaMemcpyDeviceToHost);
+      for (auto &e : ev)
+        if (abft_cuda_event_is_fatal(e.kind)) fatal_seen = true;
+      if (fatal_seen && !m) {
+        c->epoch++;
+        return -2;
+      }
+    }
+  }
+  c->epoch++;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+  if (m) {
+    // kernels past convergence never ran: take back the sequence numbers they were given, so that the
+    // next reduction / push continues consecutively (the slot parity relies on it)
+    m->seq = seq0 + 1u + 2u * (unsigned)done_iters;
+    m->epoch = epoch0 + 1u + (unsigned)done_iters;
+  }
+  if (rr_out) *rr_out = c->h_scalars[(done_iters & 1) ? SLOT_RR1 : SLOT_RR0];
+  return done_iters;
+}
+
+extern "C" {
+
 int abft_cuda_cg_solve(abft_ctx *c, abft_matrix *A, const abft_vector *b, abft_vector *x, abft_vector *r,
                        abft_vector *p, abft_vector *w, int max_itrs, double conv_threshold, int check_every,
                        double *rr_out) {
@@ -961,79 +1087,24 @@ int abft_cuda_cg_solve(abft_ctx *c, abft_matrix *A, const abft_vector *b, abft_v
     fail(-1, "cg_solve needs a whole (unpartitioned) matrix and vectors of its size", __FILE__, __LINE__);
     return -1;
   }
-  if (check_every < 1) check_every = 1;
-  if (cudaSetDevice(c->device) != cudaSuccess) return -1;
-  cudaStream_t s = c->stream;
-  int *flag0 = c->d_loop, *iters = c->d_loop + 2;
-  cudaMemsetAsync(c->d_loop, 0, sizeof(int) * 4, s);
-  c->h_loop[0] = 0;
-  c->h_loop[1] = 0;
-  // r = b ; p = r ; rr = r.r   (cg.cpp:87-91)
-  cudaMemcpyAsync(r->d, b->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(p->d, r->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s);
-  {
-    ReduceOut red = make_reduce(c, SLOT_RR0);
-    red.active = flag0;  // iteration 0 reads flag[0]
-    red.iters = iters;
-    red.threshold = conv_threshold;
-    red.max_itrs = max_itrs;
-    red.bump_iters = 0;
-    if (launch_dot(c, r->d, r->d, N, red, nullptr)) return -1;
+  return cg_solve_impl(c, nullptr, A, b, x, r, p, p, w, max_itrs, conv_threshold, check_every, rr_out);
+}
+
+int abft_cuda_dist_cg_solve(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_vector *b, abft_vector *x,
+                            abft_vector *r, abft_vector *p_local, abft_vector *p_full, abft_vector *w, int max_itrs,
+                            double conv_threshold, int check_every, double *rr_out) {
+  if (!c || !m || !A || !b || !x || !r || !p_local || !p_full || !w) {
+    fail(-1, "null argument", __FILE__, __LINE__);
+    return -1;
   }
-  c->epoch++;
-  int launched = 0;
-  int done_iters = 0;
-  bool active = true;
-  while (active && launched < max_itrs) {
-    const int batch = std::min(check_every, max_itrs - launched);
-    for (int j = 0; j < batch; j++, launched++) {
-      const int q = launched & 1;
-      const int *flag_cur = c->d_loop + q;
-      int *flag_next = c->d_loop + (q ^ 1);
-      const double *rr_cur = c->d_scalars + (q ? SLOT_RR1 : SLOT_RR0);
-      const int slot_new = q ? SLOT_RR0 : SLOT_RR1;
-      // w = A p, pw = p.w
-      if (launch_spmv(c, A, p->d, w->d, make_reduce(c, SLOT_SPMV_DOT), flag_cur)) return -1;
-      // alpha = rr / pw ; x += alpha p ; r -= alpha w ; rr_new = r.r
-      ReduceOut red = make_reduce(c, slot_new);
-      red.active = flag_next;
-      red.iters = iters;
-      red.threshold = conv_threshold;
-      red.max_itrs = max_itrs;
-      red.bump_iters = 1;
-      ScalarArg alpha{0.0, rr_cur, c->d_scalars + SLOT_SPMV_DOT};
-      if (launch_calc_xr(c, x->d, r->d, p->d, w->d, alpha, true, N, red, flag_cur)) return -1;
-      // beta = rr_new / rr ; p = r + beta p
-      ScalarArg beta{0.0, c->d_scalars + slot_new, rr_cur};
-      if (launch_calc_p(c, p->d, r->d, beta, true, N, flag_cur)) return -1;
-    }
-    // read back progress: iterations done and whether the next one would run
-    cudaMemcpyAsync(c->h_loop, c->d_loop + 2, sizeof(int), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(c->h_loop + 1, c->d_loop + (launched & 1), sizeof(int), cudaMemcpyDeviceToHost, s);
-    if (cudaStreamSynchronize(s) != cudaSuccess) {
-      fail(-1, "cg_solve: stream sync failed", __FILE__, __LINE__);
-      return -1;
-    }
-    done_iters = c->h_loop[0];
-    active = c->h_loop[1] != 0;
-    if (*c->h_flag) {
-      // a fault was logged; fatal ones stop the solve like the reference's exit(1)
-      unsigned int count = 0;
-      cudaMemcpy(&count, &c->d_log->count, sizeof count, cudaMemcpyDeviceToHost);
-      count = std::min(count, (unsigned)kLogCap);
-      std::vector<abft_event> ev(count);
-      if (count) cudaMemcpy(ev.data(), c->d_log->ev, sizeof(abft_event) * count, cudaMemcpyDeviceToHost);
-      for (auto &e : ev)
-        if (abft_cuda_event_is_fatal(e.kind)) {
-          c->epoch++;
-          return -2;
-        }
-    }
+  const int N = (int)A->view.n_rows;
+  if (!comm_ready(m) || p_full->d != m->peer_vec[m->rank] || p_local->d != p_full->d + m->row0 || p_local->N < N ||
+      (uint32_t)p_full->N < A->view.n_cols || b->N < N || x->N < N || r->N < N || w->N < N) {
+    fail(-1, "dist_cg_solve: vectors do not match the partition / exchange vector", __FILE__, __LINE__);
+    return -1;
   }
-  c->epoch++;
-  if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
-  if (rr_out) *rr_out = c->h_scalars[(done_iters & 1) ? SLOT_RR1 : SLOT_RR0];
-  return done_iters;
+  return cg_solve_impl(c, m->world > 1 ? m : nullptr, A, b, x, r, p_local, p_full, w, max_itrs, conv_threshold,
+                       check_every, rr_out);
 }
 
 }  // extern "C"

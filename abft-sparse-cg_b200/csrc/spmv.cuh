@@ -443,8 +443,10 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
           else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
           else
-            for (uint32_t base = 0; base < max_len; base += 4)
-              sum = walk_chunk<MODE, 4>(sum, base, len > base ? len - base : 0u, sc, sv, A.n_cols, x, suspect);
+            // longer rows: chunks of 4 up to this row's own length (never more than 3 slots past its end,
+            // which the over-staged window covers; the trip count may differ between lanes)
+            for (uint32_t base = 0; base < len; base += 4)
+              sum = walk_chunk<MODE, 4>(sum, base, len - base, sc, sv, A.n_cols, x, suspect);
           careful = (suspect & 1u) != 0;  // a check tripped somewhere in this row: walk it again, carefully
         }
         if (careful) {

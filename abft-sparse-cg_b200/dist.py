@@ -155,6 +155,18 @@ class DistCG:
         self.rr = rr
         return done
 
+    def solve_device(self, max_itrs: int, conv: float, check_every: int = 32):
+        """Device-resident loop (abft_cuda_dist_cg_solve): r = b, p = r, then iterate; -> (iterations, rr)."""
+        rr = C.c_double(0.0)
+        it = self.L.abft_cuda_dist_cg_solve(self.ctx.ctx, self.comm, self.A.handle, self.b.handle, self.x.handle,
+                                            self.r.handle, self.p.handle, self.p_full.handle, self.w.handle, int(max_itrs),
+                                            float(conv), int(check_every), C.byref(rr))
+        if it < 0:
+            from . import capi
+            raise RuntimeError("cuda target: dist_cg_solve failed: " + capi.last_error())
+        self.rr = rr.value
+        return it, rr.value
+
     def close(self):
         if self.comm:
             self.L.abft_cuda_comm_destroy(self.ctx.ctx, self.comm)

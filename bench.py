@@ -353,14 +353,39 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- value: K iterations, operands resident in HBM ----
+    # ---- host-driven loop (what the CGContext plugin does: two scalars to the host per iteration) ----
     start_solve()
     iterate(max(args.warmup, 3))
-    l0 = ctx.launch_count()
-    t_begin = time.time()
-    ms_total = timed(lambda: iterate(args.steps))
-    t_end = time.time()
-    launches = ctx.launch_count() - l0
+    ms_host = timed(lambda: iterate(args.steps))
+    its_host = args.steps / (ms_host * 1e-3)
+    ctx.report_faults()
+
+    # ---- value: K iterations of the device-resident loop (abft_cuda_[dist_]cg_solve: same kernels, the scalars
+    # stay on the device, one readback at the end), operands resident in HBM ----
+    if use_p2p:
+        def dev_loop(k):
+            return dcg.solve_device(k, 0.0, k)[0]
+    else:
+        if world > 1:
+            dev_loop = None          # the NCCL baseline has no device-resident loop
+        else:
+            def dev_loop(k):
+                return ctx.cg_solve_device(A, vb, x, r, p_loc, w, k, 0.0, k)[0]
+    if dev_loop is not None:
+        dev_loop(max(args.warmup, 3))
+        box = {}
+        l0 = ctx.launch_count()
+        t_begin = time.time()
+        ms_total = timed(lambda: box.update(it=dev_loop(args.steps)))
+        t_end = time.time()
+        launches = ctx.launch_count() - l0
+        assert box["it"] == args.steps, box
+    else:
+        l0 = ctx.launch_count()
+        t_begin = time.time()
+        ms_total = timed(lambda: iterate(args.steps))
+        t_end = time.time()
+        launches = ctx.launch_count() - l0
     clocks = sampler.stop(t_begin, t_end) if sampler else None
     its = args.steps / (ms_total * 1e-3)
     ctx.report_faults()
@@ -396,7 +421,10 @@ def main():
                                     % pkg.dist.exchanged_bytes(dcg.plan) if use_p2p else
                                     "NCCL all-gather of p + all-reduce of 2 scalars (baseline)"),
                        "l2": "inputs larger than L2 (matrix stream %.0f MB per GPU per iteration)" % (12 * nnz_local / 1e6),
-                       "abi": "C ABI of include/abft_cuda.h via ctypes (host scalars every iteration)"},
+                       "abi": "C ABI of include/abft_cuda.h via ctypes; value = device-resident loop "
+                              "(abft_cuda_[dist_]cg_solve), e2e / host_driven_loop = the four plugin calls per iteration"},
+            "host_driven_loop": {"value": its_host, "unit": "it/s", "ms_per_step": ms_host / args.steps,
+                                 "what": "spmv, dot, calc_xr, calc_p through the C ABI as cg.cpp drives them, operands resident"},
             "e2e": {"value": its_e2e, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "b,x uploaded from pinned host buffers + K iterations + x downloaded, all timed"},
             "gpu_launches": int(launches),
@@ -409,22 +437,6 @@ def main():
             "setup": {"generate_s": t_gen, "create_matrix_s": t_upload}}
 
     if world == 1 and rank == 0:
-        # ---- device-resident loop (no host round trips), for comparison ----
-        try:
-            vb2, x2, r2, p2, w2 = (ctx.create_vector(N) for _ in range(5))
-            ctx.upload(vb2, b_full)
-            ctx.cg_solve_device(A, vb2, x2, r2, p2, w2, 20, 0.0, 20)
-            box = {}
-            def dev():
-                box["it"], _ = ctx.cg_solve_device(A, vb2, x2, r2, p2, w2, args.steps, 0.0, args.steps)
-            ms_dev = timed(dev)
-            line["device_resident_loop"] = {"value": box["it"] / (ms_dev * 1e-3), "unit": "it/s",
-                                            "frac": (B_alg / (ms_dev / box["it"] * 1e-3) / 1e9) / peak}
-            for v in (vb2, x2, r2, p2, w2):
-                ctx.destroy_vector(v)
-        except Exception as e:                                    # pragma: no cover
-            line["device_resident_loop"] = {"error": str(e)}
-
         # ---- every ABFT mode, briefly ----
         if args.all_modes:
             modes = {}
@@ -434,19 +446,13 @@ def main():
                     continue
                 c2, A2, _ = setup(mode)
                 s2 = torch.cuda.ExternalStream(c2.L.abft_cuda_ctx_stream(c2.ctx))
-                pv, wv, xv, rv = (c2.create_vector(N) for _ in range(4))
-                c2.upload(pv, b_full); c2.upload(rv, b_full)
-                def it2(k, c2=c2, A2=A2, pv=pv, wv=wv, xv=xv, rv=rv):
-                    rr = 1.0
-                    for _ in range(k):
-                        c2.spmv(A2, pv, wv)
-                        pw = c2.dot(pv, wv)
-                        rr_new = c2.calc_xr(xv, rv, pv, wv, rr / pw if pw else 0.0)
-                        c2.calc_p(pv, rv, rr_new / rr if rr else 0.0)
-                        rr = rr_new
-                it2(5)
+                bv, xv, rv, pv, wv = (c2.create_vector(N) for _ in range(5))
+                c2.upload(bv, b_full)
+                c2.cg_solve_device(A2, bv, xv, rv, pv, wv, 5, 0.0, 5)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize(); e0.record(s2); it2(50); e1.record(s2); e1.synchronize()
+                torch.cuda.synchronize(); e0.record(s2)
+                c2.cg_solve_device(A2, bv, xv, rv, pv, wv, 50, 0.0, 50)
+                e1.record(s2); e1.synchronize()
                 ms_it = e0.elapsed_time(e1) / 50
                 e0.record(s2)
                 for _ in range(30):

@@ -221,6 +221,13 @@ int abft_cuda_dist_dot(abft_ctx *ctx, abft_comm *comm, const abft_vector *a, con
 int abft_cuda_dist_calc_xr(abft_ctx *ctx, abft_comm *comm, abft_vector *x, abft_vector *r, const abft_vector *p,
                            const abft_vector *w, double alpha, double *out);
 
+/* device-resident loop over a row partition: like abft_cuda_cg_solve, every rank calls it with the same
+ * arguments; scalars never visit the host, the exchange and the all-reduces stay inside the kernels.  A fatal
+ * fault does not stop it early (ranks wait on each other): poll the events afterwards.  Returns iterations. */
+int abft_cuda_dist_cg_solve(abft_ctx *ctx, abft_comm *comm, abft_matrix *A, const abft_vector *b, abft_vector *x,
+                            abft_vector *r, abft_vector *p_local, abft_vector *p_full, abft_vector *w, int max_itrs,
+                            double conv_threshold, int check_every, double *rr_out);
+
 /* ---- introspection for bench.py / tests ---- */
 /* number of kernels this library has launched on the context since creation */
 uint64_t abft_cuda_launch_count(const abft_ctx *ctx);

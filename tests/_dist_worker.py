@@ -119,10 +119,24 @@ def main():
         hist = []
         it = cg.iterate(2000, 1e-10, hist)
         lines = ctx.report_faults()
-        xs = all_gather(ctx.download(cg.x))
+        x_host_loop = ctx.download(cg.x)
+        rr_host_loop = cg.rr
+        xs = all_gather(x_host_loop)
         all_lines = all_gather(lines)
-        result = dict(iterations=it, rr=cg.rr, x=np.concatenate(xs).tolist(), hist=hist, lines=all_lines, cuts=cuts,
-                      plan=cg.plan, e0_last=e0)
+        # the device-resident loop over the same partition: same kernels, same scalars -> identical bits
+        dev_same = []
+        for every in (1, 16):
+            ctx.upload(cg.x, np.zeros(r1 - r0))
+            it2, rr2 = cg.solve_device(2000, 1e-10, every)
+            dev_same.append(bool(it2 == it and rr2 == rr_host_loop and np.array_equal(ctx.download(cg.x), x_host_loop)))
+        # and a host-driven solve still works afterwards (sequence numbers were handed back correctly)
+        ctx.upload(cg.x, np.zeros(r1 - r0))
+        cg.start()
+        it3 = cg.iterate(2000, 1e-10)
+        dev_same.append(bool(it3 == it and np.array_equal(ctx.download(cg.x), x_host_loop)))
+        ctx.report_faults()
+        result = dict(iterations=it, rr=rr_host_loop, x=np.concatenate(xs).tolist(), hist=hist, lines=all_lines, cuts=cuts,
+                      plan=cg.plan, e0_last=e0, dev_same=all_gather(dev_same))
         cg.close()
         ctx.close()
     results = all_gather(dict(iterations=result["iterations"], rr=result["rr"]))

@@ -38,6 +38,8 @@ def test_dist_cg_matches_oracle(pkg, O, tmp_path, shape, mode):
         assert np.max(np.abs(hist - ref["rr_hist"]) / ref["rr_hist"]) <= 1e-10
         assert np.max(np.abs(x - ref["x"])) <= 1e-10 * np.max(np.abs(ref["x"]))
     assert all(lines == [] for lines in res["lines"])
+    # device-resident partitioned loop == host-driven partitioned loop, bit for bit, on every rank
+    assert all(all(flags) for flags in res["dev_same"]), res["dev_same"]
 
 
 def test_dist_fault_reports_global_index(pkg, O, tmp_path):

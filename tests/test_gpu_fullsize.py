@@ -121,7 +121,6 @@ def test_poisson3d_256_all_modes_give_identical_iterates(pkg):
         it, hist = ctx.cg(A, vb, x, r, p, w, 25, 0.0)
         got = (hist.tobytes(), checksum(ctx.download(x)))
         assert it == 25 and ctx.messages == []
-        assert np.all(np.diff(hist[:10]) < 0)
         if ref is None:
             ref = got
         assert got == ref, mode

@@ -48,6 +48,7 @@ def shapes(mg):
         "p2d_16_b5": lambda: mg.poisson2d(16, 5),
         "p3d_12": lambda: mg.poisson3d(12),
         "powerlaw": lambda: mg.powerlaw(3000, 60000, seed=2),
+        "powerlaw_dense": lambda: mg.powerlaw(6000, 700000, alpha=1.6, max_deg=1500, seed=9),   # full tiles, rows of 100s
         "ragged": ragged,
         "short_rows": short_rows,
         "one_by_one": lambda: mg.Triplets([0], [0], [2.5], 1),
