@@ -34,6 +34,7 @@ namespace abft {
 constexpr int kTileNnz = 2048;
 constexpr int kTileRows = kBlock;  // 256: one row per thread
 constexpr int kStages = 2;
+constexpr uint32_t kSeqRowMax = 32;  // irregular tiles: rows up to this long are summed sequentially by one thread
 constexpr uint32_t kOverrun = 8;  // elements staged past a tile's end (>= longest unrolled walk - 1)
 
 constexpr uint32_t kTileRegular = 1u << 16;  // info flag: thread-per-row path
@@ -252,6 +253,18 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
   return sum;
 }
 
+// CONSTRAINTS, warp-collective: true iff no element of the row violates `col < N` or the strict
+// column order (CSR/CPUContext.cpp:188-200).  cols points at the row's first staged column word.
+__device__ __forceinline__ bool constraints_fast_ok_row(const uint32_t *cols, uint32_t len, uint32_t n_cols, int lane) {
+  bool bad = false;
+  for (uint32_t i = lane; i < len; i += 32) {
+    const uint32_t c = cols[i];
+    bad |= (c >= n_cols);
+    if (i + 1 < len) bad |= (cols[i + 1] <= c);
+  }
+  return !__any_sync(0xffffffffu, bad);
+}
+
 // CRC-32C of one 32-bit word appended to a running (raw) state; slicing-by-4 tables
 // tab[s*256 + b] in shared memory.
 __device__ __forceinline__ uint32_t crc_word(uint32_t crc, uint32_t w, const uint32_t *tab) {
@@ -409,8 +422,32 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         dot_part = __dadd_rn(dot_part, __dmul_rn(total, x[A.row_offset + t.row_begin]));
       }
     } else {
-      const bool row_mapped = (t.info & kTileRegular) || MODE == ABFT_MODE_CRC32C || MODE == ABFT_MODE_CONSTRAINTS;
-      if (!row_mapped) {
+      const bool irregular = !(t.info & kTileRegular) && MODE != ABFT_MODE_CRC32C;
+      // CONSTRAINTS, one row, exactly the reference's checks in the reference's order
+      // (CSR/CPUContext.cpp:173-182 row checks, :184-203 element checks); returns the row sum
+      auto constraints_careful = [&](uint32_t grow, uint32_t rs, uint32_t re) -> double {
+        double sum = 0.0;
+        if (re > A.nnz) log_event(L, ABFT_EV_ROW_SIZE, A.row_offset + grow, 0);
+        else if (re < rs) log_event(L, ABFT_EV_ROW_ORDER, A.row_offset + grow, 0);
+        else
+          for (uint32_t i = rs; i < re; i++) {
+            // elements normally sit in the staged window; a corrupted row pointer can send the row
+            // outside it, then go to global memory (i < nnz was checked above)
+            const bool in = (i >= t.nnz_begin) && (i < t.nnz_end);
+            const uint32_t col = in ? B.cols[i - cb] : A.cols[i];
+            if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + grow); break; }
+            if (i < re - 1) {
+              const bool in2 = (i + 1 >= t.nnz_begin) && (i + 1 < t.nnz_end);
+              const uint32_t nxt = in2 ? B.cols[i + 1 - cb] : A.cols[i + 1];
+              if (nxt <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + grow); break; }
+            }
+            // (the staged values of an irregular tile have been overwritten by products)
+            const double val = (in && !irregular) ? B.vals[i - vb] : A.values[i];
+            sum = __dadd_rn(sum, __dmul_rn(val, __ldg(x + col)));
+          }
+        return sum;
+      };
+      if (irregular) {
         // ---------------- irregular tile, element phase: product -> shared memory (in place) ----------------
         double *prod = const_cast<double *>(B.vals);
         for (uint32_t e = tid; e < n; e += kBlock) {
@@ -423,6 +460,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         uint32_t rs = B.rptr[row - rb], re = B.rptr[row + 1 - rb];
         double sum = 0.0;
         bool careful = true;
+        bool long_row = false;  // irregular tile: left to the warp-per-row pass
         if (MODE != ABFT_MODE_CONSTRAINTS) {
           // these modes trust rows[] like the reference; clamp so a bad pointer cannot fault
           rs = min(max(rs, t.nnz_begin), t.nnz_end);
@@ -451,25 +489,22 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         }
         if (careful) {
           sum = 0.0;
-          if (MODE == ABFT_MODE_CONSTRAINTS) {
-            // CSR/CPUContext.cpp:173-182, then :184-203
-            if (re > A.nnz) log_event(L, ABFT_EV_ROW_SIZE, A.row_offset + row, 0);
-            else if (re < rs) log_event(L, ABFT_EV_ROW_ORDER, A.row_offset + row, 0);
-            else
+          if (MODE == ABFT_MODE_CONSTRAINTS && irregular && rs >= t.nnz_begin && re <= t.nnz_end && rs <= re) {
+            // irregular tile: products are staged; check the columns while adding them up
+            if (re - rs <= kSeqRowMax) {
+              bool bad = false;
               for (uint32_t i = rs; i < re; i++) {
-                // elements normally sit in the staged window; a corrupted row pointer can send the
-                // row outside it, then go to global memory (i < nnz was checked above)
-                const bool in = (i >= t.nnz_begin) && (i < t.nnz_end);
-                const uint32_t col = in ? B.cols[i - cb] : A.cols[i];
-                if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + row); break; }
-                if (i < re - 1) {
-                  const bool in2 = (i + 1 >= t.nnz_begin) && (i + 1 < t.nnz_end);
-                  const uint32_t nxt = in2 ? B.cols[i + 1 - cb] : A.cols[i + 1];
-                  if (nxt <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + row); break; }
-                }
-                const double val = in ? B.vals[i - vb] : A.values[i];
-                sum = __dadd_rn(sum, __dmul_rn(val, __ldg(x + col)));
+                const uint32_t col = B.cols[i - cb];
+                bad |= (col >= A.n_cols);
+                if (i + 1 < re) bad |= (B.cols[i + 1 - cb] <= col);
+                sum = __dadd_rn(sum, B.vals[i - vb]);
               }
+              if (bad) sum = constraints_careful(row, rs, re);
+            } else {
+              long_row = true;
+            }
+          } else if (MODE == ABFT_MODE_CONSTRAINTS) {
+            sum = constraints_careful(row, rs, re);
           } else if (MODE == ABFT_MODE_CRC32C) {
             const uint32_t len = re - rs;
             uint32_t crc = 0xFFFFFFFFu, stored = 0;
@@ -498,13 +533,50 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
             for (uint32_t i = rs; i < re; i++)
               sum = __dadd_rn(sum, element_product<MODE>(B.cols[i - cb], B.vals[i - vb], i, A, x, L));
           } else {
-            // ---------------- irregular tile, row phase: add the products in element order ----------------
+            // ---------------- irregular tile, row phase (short rows): add the products in element order ----------------
+            // (rows longer than kSeqRowMax are left to the warp-per-row pass below)
+            if (re - rs <= kSeqRowMax) {
 #pragma unroll 4
-            for (uint32_t i = rs; i < re; i++) sum = __dadd_rn(sum, B.vals[i - vb]);
+              for (uint32_t i = rs; i < re; i++) sum = __dadd_rn(sum, B.vals[i - vb]);
+            } else {
+              long_row = true;
+            }
           }
         }
-        y[row] = sum;
-        dot_part = __dadd_rn(dot_part, __dmul_rn(sum, x[A.row_offset + row]));
+        if (!long_row) {
+          y[row] = sum;
+          dot_part = __dadd_rn(dot_part, __dmul_rn(sum, x[A.row_offset + row]));
+        }
+      }
+      if (irregular) {
+        // ---------------- irregular tile, long rows: one warp per row, lane-strided partial sums + a fixed
+        // shuffle tree (deterministic; not the sequential order, so not bit-identical to the CPU sum) ----------------
+        const int lane = tid & 31, warp = tid >> 5;
+        for (uint32_t r2 = warp; r2 < nrows; r2 += kBlock / 32) {
+          const uint32_t grow = t.row_begin + r2;
+          uint32_t rs = B.rptr[grow - rb], re = B.rptr[grow + 1 - rb];
+          if (MODE != ABFT_MODE_CONSTRAINTS) {
+            rs = min(max(rs, t.nnz_begin), t.nnz_end);
+            re = min(max(re, rs), t.nnz_end);
+          }
+          // same admission test as the per-thread pass: inside the window, longer than kSeqRowMax
+          if (!(rs >= t.nnz_begin && re <= t.nnz_end && rs <= re) || re - rs <= kSeqRowMax) continue;
+          if (MODE == ABFT_MODE_CONSTRAINTS && !constraints_fast_ok_row(B.cols + (rs - cb), re - rs, A.n_cols, lane)) {
+            if (lane == 0) {
+              const double sum = constraints_careful(grow, rs, re);
+              y[grow] = sum;
+              dot_part = __dadd_rn(dot_part, __dmul_rn(sum, x[A.row_offset + grow]));
+            }
+            continue;
+          }
+          double part = 0.0;
+          for (uint32_t i = rs + lane; i < re; i += 32) part = __dadd_rn(part, B.vals[i - vb]);
+          part = warp_sum(part);
+          if (lane == 0) {
+            y[grow] = part;
+            dot_part = __dadd_rn(dot_part, __dmul_rn(part, x[A.row_offset + grow]));
+          }
+        }
       }
     }
     __syncthreads();  // everyone is done with stage `st`: it may be refilled
