@@ -35,6 +35,7 @@ SYMBOLS = [
     "abft_cuda_comm_window_ptr", "abft_cuda_comm_attach_self", "abft_cuda_comm_attach_peer",
     "abft_cuda_comm_attach_peer_ptrs", "abft_cuda_comm_set_plan", "abft_cuda_dist_push", "abft_cuda_dist_calc_p",
     "abft_cuda_dist_spmv", "abft_cuda_dist_dot", "abft_cuda_dist_calc_xr", "abft_cuda_dist_cg_solve",
+    "abft_cuda_dist_dot_async", "abft_cuda_dist_calc_xr_async",
 ]
 
 
@@ -125,6 +126,8 @@ def load():
     sig("abft_cuda_dist_spmv", i32, vp, vp, vp, vp, vp)
     sig("abft_cuda_dist_dot", i32, vp, vp, vp, vp, f64p)
     sig("abft_cuda_dist_calc_xr", i32, vp, vp, vp, vp, vp, vp, f64, f64p)
+    sig("abft_cuda_dist_dot_async", i32, vp, vp, vp, vp, i32p)
+    sig("abft_cuda_dist_calc_xr_async", i32, vp, vp, vp, vp, vp, vp, f64, i32p)
     sig("abft_cuda_dist_cg_solve", i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, i32, f64p)
     _lib = L
     return L

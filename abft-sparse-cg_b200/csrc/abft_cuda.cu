@@ -853,6 +853,12 @@ static int comm_ready(abft_comm *m) {
   return 1;
 }
 
+static int comm_windows_ready(abft_comm *m) {
+  for (int s = 0; s < m->world; s++)
+    if (!m->win[s]) return 0;
+  return 1;
+}
+
 template <bool COMPUTE>
 static int launch_push(abft_ctx *c, abft_comm *m, abft_vector *p_local, const abft_vector *r, double beta) {
   REQUIRE(comm_ready(m), "comm: a peer has not been attached");
@@ -913,22 +919,43 @@ int abft_cuda_dist_spmv(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_ve
   return 0;
 }
 
-int abft_cuda_dist_dot(abft_ctx *c, abft_comm *m, const abft_vector *a, const abft_vector *b, double *out) {
-  REQUIRE(c && m && a && b && out, "null argument");
+// asynchronous: *slot_out tells where the (global) value will be once the stream has drained
+int abft_cuda_dist_dot_async(abft_ctx *c, abft_comm *m, const abft_vector *a, const abft_vector *b, int *slot_out) {
+  REQUIRE(c && m && a && b && slot_out, "null argument");
+  REQUIRE(comm_windows_ready(m), "comm: a peer window has not been attached");
   CK(cudaSetDevice(c->device));
-  int slot = SLOT_DOT;
   const bool fused = c->dot_epoch == c->epoch && a->N == c->dot_n && b->N >= a->N &&
                      ((a->d == c->dot_a && b->d == c->dot_b) || (a->d == c->dot_b && b->d == c->dot_a));
   if (fused) {
-    slot = SLOT_SPMV_DOT;  // dist_spmv already reduced it over all ranks
-  } else {
-    REQUIRE(b->N >= a->N, "dot: second vector shorter than the first");
-    int rc = launch_dot(c, a->d, b->d, a->N, make_reduce(c, SLOT_DOT, m), nullptr);
-    if (rc) return rc;
+    *slot_out = SLOT_SPMV_DOT;  // dist_spmv already reduced it over all ranks
+    return 0;
   }
+  REQUIRE(b->N >= a->N, "dot: second vector shorter than the first");
+  *slot_out = SLOT_DOT;
+  return launch_dot(c, a->d, b->d, a->N, make_reduce(c, SLOT_DOT, m), nullptr);
+}
+
+int abft_cuda_dist_dot(abft_ctx *c, abft_comm *m, const abft_vector *a, const abft_vector *b, double *out) {
+  REQUIRE(out, "null argument");
+  int slot = SLOT_DOT;
+  int rc = abft_cuda_dist_dot_async(c, m, a, b, &slot);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));
   *out = c->h_scalars[slot];
   return 0;
+}
+
+int abft_cuda_dist_calc_xr_async(abft_ctx *c, abft_comm *m, abft_vector *x, abft_vector *r, const abft_vector *p,
+                                 const abft_vector *w, double alpha, int *slot_out) {
+  REQUIRE(c && m && x && r && p && w && slot_out, "null argument");
+  REQUIRE(comm_windows_ready(m), "comm: a peer window has not been attached");
+  REQUIRE(r->N >= x->N && p->N >= x->N && w->N >= x->N, "calc_xr: vector lengths");
+  CK(cudaSetDevice(c->device));
+  ScalarArg a{alpha, nullptr, nullptr};
+  *slot_out = SLOT_XR;
+  int rc = launch_calc_xr(c, x->d, r->d, p->d, w->d, a, false, x->N, make_reduce(c, SLOT_XR, m), nullptr);
+  c->epoch++;
+  return rc;
 }
 
 int abft_cuda_dist_calc_xr(abft_ctx *c, abft_comm *m, abft_vector *x, abft_vector *r, const abft_vector *p,

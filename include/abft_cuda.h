@@ -220,6 +220,12 @@ int abft_cuda_dist_spmv(abft_ctx *ctx, abft_comm *comm, abft_matrix *mat, const 
 int abft_cuda_dist_dot(abft_ctx *ctx, abft_comm *comm, const abft_vector *a, const abft_vector *b, double *out);
 int abft_cuda_dist_calc_xr(abft_ctx *ctx, abft_comm *comm, abft_vector *x, abft_vector *r, const abft_vector *p,
                            const abft_vector *w, double alpha, double *out);
+/* Asynchronous halves, for one host thread driving several GPUs (host/CUDAContext.cpp with ABFT_CUDA_NGPUS):
+ * the reduction of rank r only completes once every rank has launched its part, so all launches must be issued
+ * before the first sync.  *slot_out: read abft_cuda_scalar_host(ctx, slot) after abft_cuda_ctx_sync. */
+int abft_cuda_dist_dot_async(abft_ctx *ctx, abft_comm *comm, const abft_vector *a, const abft_vector *b, int *slot_out);
+int abft_cuda_dist_calc_xr_async(abft_ctx *ctx, abft_comm *comm, abft_vector *x, abft_vector *r, const abft_vector *p,
+                                 const abft_vector *w, double alpha, int *slot_out);
 
 /* device-resident loop over a row partition: like abft_cuda_cg_solve, every rank calls it with the same
  * arguments; scalars never visit the host, the exchange and the all-reduces stay inside the kernels.  A fatal

@@ -126,3 +126,38 @@ def test_unknown_mode_fails_like_the_reference(O, exe, mtx32):
     # CGContext.cpp:18-23
     code, text = O.run_cg_csr(exe, ["-f", mtx32, "-t", "cuda", "-m", "bogus"])
     assert code == 1 and "No implementation found for cuda-bogus" in text
+
+
+# ---------------------------------------------------------------- multi-GPU through the same CLI
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("mode", ["none", "secded", "constraints", "crc32c"])
+def test_multi_gpu_cli_matches_cpu_target(O, exe, mtx256, mode):
+    """ABFT_CUDA_NGPUS=g: the plugin row-partitions the matrix over g GPUs of the box; same output as -t cpu."""
+    g = min(_ngpus(), 4)
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    args = ["-f", mtx256, "-b", "1", "-c", "1e-10", "-m"]
+    code, text = O.run_cg_csr(exe, args + [mode, "-t", "cuda"], env_extra={"ABFT_CUDA_NGPUS": str(g)})
+    assert code == 0, text[-2000:]
+    code0, text0 = O.run_cg_csr(exe, args + [mode if mode != "crc32c" else "none", "-t", "cpu"])
+    assert field(text, "ran for") == field(text0, "ran for") == "ran for 683 iterations"
+    assert field(text, "total error") == field(text0, "total error")
+    assert field(text, "max error") == field(text0, "max error")
+
+
+def test_multi_gpu_cli_fixture_replay(O, exe, mtx32, golden_cli):
+    """The pinned-seed injection fixtures with the matrix split over the GPUs: same flips (routed to the owning
+    GPU), same messages with global indices, same exit status."""
+    g = min(_ngpus(), 4)
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    for case in golden_cli["cases"]:
+        args = ["-f", mtx32, "-b", str(golden_cli["blocks"]), "-c", "1e-10", "-i", "300", "-t", "cuda", "-m", case["mode"]]
+        code, text = O.run_cg_csr(exe, args + case["extra"], fake_time=case["seed"], env_extra={"ABFT_CUDA_NGPUS": str(g)})
+        assert faults(text) == case["faults"], (case, text[-1500:])
+        assert code == case["exit"], case
+        assert field(text, "ran for") == case["ran"], case
