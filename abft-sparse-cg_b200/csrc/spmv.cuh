@@ -242,14 +242,19 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
       suspect = or_suspect_bits<MODE>(suspect, w0, w1, c[k]);
     }
     const uint32_t col = ModeTraits<MODE>::masks_column ? (c[k] & 0x00FFFFFFu) : c[k];
-    // a column no check caught can point outside vec[] (the reference reads out of bounds: UB; here
-    // the element contributes nothing): gather from a clamped address, drop the product below
-    ok[k] = ((uint32_t)k < count) && (col < n_cols);
+    // A column no check caught can point outside vec[] (the reference reads out of bounds: UB): the
+    // gather address is clamped.  Mode none also drops the product, as the oracle does; in the checked
+    // modes an out-of-range column either trips `suspect` (constraints) or belongs to a multi-bit fault
+    // the code cannot see at all, so the fast walk does not spend a compare on it.
+    ok[k] = ((uint32_t)k < count) && (MODE != ABFT_MODE_NONE || col < n_cols);
     xv[k] = __ldg(x + min(col, n_cols - 1u));
   }
 #pragma unroll
-  for (int k = 0; k < LEN; k++)
-    if (ok[k]) sum = __dadd_rn(sum, __dmul_rn(v[k], xv[k]));
+  for (int k = 0; k < LEN; k++) {
+    // predicated add (not a select between sum and sum + prod: that costs two FSEL per element)
+    const double prod = __dmul_rn(v[k], xv[k]);
+    asm("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p add.rn.f64 %0, %0, %1;\n}" : "+d"(sum) : "d"(prod), "r"((uint32_t)ok[k]));
+  }
   return sum;
 }
 
