@@ -92,11 +92,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// The matrix stream is read exactly once per spmv: tag it evict-first in L2 so that it does not push
+// out vec[], which every row block re-reads (7-point stencil: each entry is gathered by 7 rows spread
+// over ~11 MB of stream).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 
 __device__ __forceinline__ void split_value(double v, uint32_t &w0, uint32_t &w1) {
@@ -323,6 +332,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     for (int i = tid; i < 1024; i += kBlock) s_crc[i] = g_crc_tab[i];
   __syncthreads();
 
+  const uint64_t stream_policy = l2_evict_first_policy();
   // producer (thread 0): stream tile `t` into stage `s`
   auto issue = [&](int s, const Tile &t) {
     StageBuf &B = stage[s];
@@ -339,10 +349,10 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&s_full[s], rbytes + cbytes + vbytes);
-    bulk_g2s(B.rptr, A.rowptr + rb, rbytes, &s_full[s]);
+    bulk_g2s(B.rptr, A.rowptr + rb, rbytes, &s_full[s], stream_policy);
     if (cbytes) {
-      bulk_g2s(B.cols, A.cols + cb, cbytes, &s_full[s]);
-      bulk_g2s(B.vals, A.values + vb, vbytes, &s_full[s]);
+      bulk_g2s(B.cols, A.cols + cb, cbytes, &s_full[s], stream_policy);
+      bulk_g2s(B.vals, A.values + vb, vbytes, &s_full[s], stream_policy);
     }
   };
 
