@@ -66,18 +66,26 @@ calc_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__r
   const double2 *p2 = reinterpret_cast<const double2 *>(p);
   const double2 *w2 = reinterpret_cast<const double2 *>(w);
   double acc = 0.0;
-  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n2; i += gridDim.x * kBlock) {
-    double2 xv = x2[i], rv = r2[i];
-    const double2 pv = p2[i], wv = w2[i];
-    xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
-    xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
-    rv.x = __dsub_rn(rv.x, __dmul_rn(alpha, wv.x));
-    rv.y = __dsub_rn(rv.y, __dmul_rn(alpha, wv.y));
-    x2[i] = xv;
-    r2[i] = rv;
-    acc = __dadd_rn(acc, __dmul_rn(rv.x, rv.x));
-    acc = __dadd_rn(acc, __dmul_rn(rv.y, rv.y));
-  }
+  // Swept from the END of the vectors towards the front: spmv has just written w (and gathered p) front to
+  // back, so their tails are what the 126 MB L2 still holds; calc_p then runs front to back again and finds
+  // the head of r this kernel wrote last.  (Fixed per kernel, so results do not depend on call history.)
+  const int stride = gridDim.x * kBlock;
+  const int first = blockIdx.x * kBlock + threadIdx.x;
+  if (first < n2)
+    for (int i = first + ((n2 - 1 - first) / stride) * stride; i >= first; i -= stride) {
+      // x is touched by no other kernel of the iteration, w is dead after this read: stream them through
+      // L2 (evict-first) so that r and p, which calc_p and the next spmv want, stay
+      double2 xv = __ldcs(x2 + i), rv = r2[i];
+      const double2 pv = p2[i], wv = __ldcs(w2 + i);
+      xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
+      xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
+      rv.x = __dsub_rn(rv.x, __dmul_rn(alpha, wv.x));
+      rv.y = __dsub_rn(rv.y, __dmul_rn(alpha, wv.y));
+      __stcs(x2 + i, xv);
+      r2[i] = rv;
+      acc = __dadd_rn(acc, __dmul_rn(rv.x, rv.x));
+      acc = __dadd_rn(acc, __dmul_rn(rv.y, rv.y));
+    }
   for (int i = 2 * n2 + blockIdx.x * kBlock + threadIdx.x; i < N; i += gridDim.x * kBlock) {
     const double xn = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
     const double rn = __dsub_rn(r[i], __dmul_rn(alpha, w[i]));
