@@ -111,17 +111,6 @@ static int ensure_tables(int device) {
   for (int s = 0; s < 4; s++)
     for (uint32_t i = 0; i < 256; i++) tab[s * 256 + i] = crc32c_table_entry(i, s);
   CK(cudaMemcpyToSymbol(g_crc_tab, tab.data(), sizeof(uint32_t) * 1024));
-  // three wider slices of the same linear step F(x) = T3[x0] ^ T2[x1] ^ T1[x2] ^ T0[x3]
-  auto F = [&](uint32_t x) {
-    return tab[768 + (x & 0xFF)] ^ tab[512 + ((x >> 8) & 0xFF)] ^ tab[256 + ((x >> 16) & 0xFF)] ^ tab[x >> 24];
-  };
-  std::vector<uint32_t> tab3(kCrcTab3Words);
-  for (uint32_t v = 0; v < 2048; v++) {
-    tab3[v] = F(v);
-    tab3[2048 + v] = F(v << 11);
-  }
-  for (uint32_t v = 0; v < 1024; v++) tab3[4096 + v] = F(v << 22);
-  CK(cudaMemcpyToSymbol(g_crc_tab3, tab3.data(), sizeof(uint32_t) * kCrcTab3Words));
   if (device >= 0 && device < 64) g_tables_ready[device] = true;
   return 0;
 }

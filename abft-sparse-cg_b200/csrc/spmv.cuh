@@ -288,16 +288,6 @@ __device__ __forceinline__ uint32_t crc_word(uint32_t crc, uint32_t w, const uin
 
 __device__ uint32_t g_crc_tab[1024];  // filled by the host at library init
 
-// The same step with three wider slices (11 + 11 + 10 bits of crc ^ word): 3 shared-memory lookups per word
-// instead of 4.  The spmv check is bound by shared-memory wavefronts (table lookups + their bank conflicts,
-// profiles/r1_ncu_full_spmv_crc32c_256cube.txt), so fewer, wider lookups win.  tab = [2048 | 2048 | 1024].
-constexpr int kCrcTab3Words = 2048 + 2048 + 1024;
-__device__ __forceinline__ uint32_t crc_word3(uint32_t crc, uint32_t w, const uint32_t *tab) {
-  const uint32_t x = crc ^ w;
-  return tab[x & 0x7FFu] ^ tab[2048 + ((x >> 11) & 0x7FFu)] ^ tab[4096 + (x >> 22)];
-}
-__device__ uint32_t g_crc_tab3[kCrcTab3Words];  // filled by the host at library init
-
 // multi-GPU: the peers whose pushes into vec[] must have landed before it is read
 struct WaitSpec {
   const CommWindow *me;  // local window
@@ -317,7 +307,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   StageBuf *stage = reinterpret_cast<StageBuf *>(dyn_smem);
   __shared__ __align__(8) uint64_t s_full[kStages];
   __shared__ Tile s_tile[kStages];
-  __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? kCrcTab3Words : 1];
+  __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? 1024 : 1];
   __shared__ double s_warp[kBlock / 32];
 
   if (active && *active == 0) return;  // device-resident loop already converged
@@ -339,7 +329,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   __syncthreads();
   if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (MODE == ABFT_MODE_CRC32C)
-    for (int i = tid; i < kCrcTab3Words; i += kBlock) s_crc[i] = g_crc_tab3[i];
+    for (int i = tid; i < 1024; i += kBlock) s_crc[i] = g_crc_tab[i];
   __syncthreads();
 
   const uint64_t stream_policy = l2_evict_first_policy();
@@ -435,9 +425,9 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           uint32_t w0, w1;
           split_value(A.values[i], w0, w1);
           if (e < 4) stored |= (cw >> 24) << (8 * e);
-          crc = crc_word3(crc, w0, s_crc);
-          crc = crc_word3(crc, w1, s_crc);
-          crc = crc_word3(crc, cw & 0x00FFFFFFu, s_crc);
+          crc = crc_word(crc, w0, s_crc);
+          crc = crc_word(crc, w1, s_crc);
+          crc = crc_word(crc, cw & 0x00FFFFFFu, s_crc);
         }
         if ((crc ^ 0xFFFFFFFFu) != stored) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + t.row_begin, 0);
       }
@@ -541,9 +531,9 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
               split_value(val, w0, w1);
               if (len >= 4) {
                 if (i - rs < 4) stored |= (cw >> 24) << (8 * (i - rs));
-                crc = crc_word3(crc, w0, s_crc);
-                crc = crc_word3(crc, w1, s_crc);
-                crc = crc_word3(crc, cw & 0x00FFFFFFu, s_crc);
+                crc = crc_word(crc, w0, s_crc);
+                crc = crc_word(crc, w1, s_crc);
+                crc = crc_word(crc, cw & 0x00FFFFFFu, s_crc);
               } else {
                 // too short to hold 32 CRC bits: SECDED check byte per element, detect-only
                 if ((overall_parity(w0, w1, cw) | syndrome7_any(w0, w1, cw)) & 1u) bad = true;
