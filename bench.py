@@ -113,6 +113,17 @@ class ClockSampler:
                 "samples_total": total, "reasons": sorted(reasons)}
 
 
+def ncu_traffic(mode, workload, grid, world):
+    """DRAM bytes (read + write) of one spmv launch from the committed ncu capture of this workload/mode
+    (profiles/r1_spmv_dram_traffic.json), or None when there is no capture for it."""
+    path = os.path.join(ROOT, "profiles", "r1_spmv_dram_traffic.json")
+    if workload != "poisson3d" or grid != 256 or world != 1 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    return d.get(mode, {}).get("traffic")
+
+
 def slab_triplets(mg, grid, r0, r1):
     """Rows [r0, r1) of the grid^3 7-point Poisson matrix, global columns, cg.cpp order."""
     n = grid
@@ -429,7 +440,8 @@ def main():
                     "what": "b,x uploaded from pinned host buffers + K iterations + x downloaded, all timed"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": f"spmv_kernel<{args.mode}>", "achieved": spmv_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": spmv_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": spmv_gbs / peak,
+                         "traffic": ncu_traffic(args.mode, args.workload, args.grid, world), "peak_source": peak_src,
                          "bytes_per_launch": B_spmv // world, "ms_per_launch": ms_spmv},
             "roofline_cg_iteration": {"bound": "hbm", "bytes_per_iteration": B_alg // world, "achieved": iter_gbs,
                                       "peak": peak, "unit": "GB/s", "frac": iter_gbs / peak},
