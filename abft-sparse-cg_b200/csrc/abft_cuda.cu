@@ -699,7 +699,9 @@ int abft_cuda_poll_events(abft_ctx *c, abft_event *out, int cap, int *fatal) {
   std::vector<abft_event> ev(count);
   if (count && cudaMemcpy(ev.data(), c->d_log->ev, sizeof(abft_event) * count, cudaMemcpyDeviceToHost) != cudaSuccess)
     return -1;
-  cudaMemset(c->d_log, 0, sizeof(unsigned int) * 2);
+  // on the context's own (non-blocking) stream: a legacy-stream memset would not be ordered before the next kernel
+  cudaMemsetAsync(c->d_log, 0, sizeof(unsigned int) * 2, c->stream);
+  cudaStreamSynchronize(c->stream);
   *c->h_flag = 0;
 
   // serial order of the reference: rows ascending; within a row the row checks
