@@ -454,3 +454,53 @@ def test_row_partitions_reproduce_the_whole(pkg, O, mode):
     exact = O.lib().orc_dot(vec, y0, t.N)
     assert abs(total_dot - exact) <= RTOL * abs(exact)
     ctx.close()
+
+
+# ---------------------------------------------------------------- exhaustive flip sweeps
+def test_secded_detects_all_4560_double_flips(pkg):
+    """Every pair of bits of one element: parity even, syndrome non-zero -> 'double-bit error detected', nothing
+    corrected, nothing written back."""
+    t = pkg.matgen.poisson2d(3)
+    ctx = pkg.CUDAContext("secded")
+    A = ctx.create_matrix(t.cols, t.rows, t.vals, t.N)
+    clean_cols, _, clean_vals = ctx.read_matrix(A)
+    v, w = ctx.create_vector(t.N), ctx.create_vector(t.N)
+    ctx.upload(v, np.ones(t.N))
+    index = 7
+    n = 0
+    for a in range(96):
+        for b in range(a + 1, 96):
+            ctx.flip_bit(A, index, a); ctx.flip_bit(A, index, b)
+            ctx.spmv(A, v, w)
+            events, fatal = ctx.poll_events()
+            assert fatal and events == [(4, index, 0)], (a, b, events)
+            ctx.flip_bit(A, index, a); ctx.flip_bit(A, index, b)        # undo
+            n += 1
+    assert n == 4560
+    cols, _, vals = ctx.read_matrix(A)
+    assert np.array_equal(cols, clean_cols) and np.array_equal(vals, clean_vals)
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["sec7", "sec8"])
+def test_all_double_flips_match_oracle(pkg, O, mode):
+    """SEC7/SEC8 mis-correct double flips (768 of the 4560 pairs even point at 'bit >= 96', where the reference
+    writes out of bounds): the CUDA target must report exactly what the oracle reports and leave the same matrix.
+    One element per pair in a diagonal matrix, one spmv per batch (the device log holds 2048 records)."""
+    pairs = [(a, b) for a in range(96) for b in range(a + 1, 96)]
+    rng = np.random.default_rng(12)
+    for lo in range(0, len(pairs), 1500):
+        batch = pairs[lo:lo + 1500]
+        n = len(batch)
+        t = pkg.matgen.Triplets(np.arange(n), np.arange(n), rng.standard_normal(n) * 3.0, n)
+        ctx, A, om = make(pkg, O, mode, t)
+        for i, (a, b) in enumerate(batch):
+            for bit in (a, b):
+                ctx.flip_bit(A, i, bit); om.flip(i, bit)
+        y, fatal, events, _ = gpu_spmv(ctx, A, np.ones(n))
+        y0, fatal0, ev0 = om.spmv(np.ones(n))
+        assert (fatal, events) == (fatal0, ev0)
+        cols, _, vals = ctx.read_matrix(A)
+        assert np.array_equal(cols, om.cols) and np.array_equal(vals.view(np.uint64), om.values.view(np.uint64))
+        assert np.array_equal(y.view(np.uint64), y0.view(np.uint64))
+        ctx.close()
