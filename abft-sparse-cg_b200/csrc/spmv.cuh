@@ -211,8 +211,8 @@ __device__ __forceinline__ double element_product(uint32_t cw, double v, uint32_
     }
   }
   const uint32_t col = ModeTraits<MODE>::masks_column ? (cw & 0x00FFFFFFu) : cw;
-  // a column no check caught can point outside vec[] (the reference reads out of bounds: UB)
-  const double xv = (col < A.n_cols) ? __ldg(x + col) : 0.0;
+  // a column no check caught can point outside vec[] (the reference reads out of bounds: UB): clamp it
+  const double xv = __ldg(x + min(col, A.n_cols - 1u));
   return __dmul_rn(v, xv);
 }
 
@@ -251,11 +251,10 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
       suspect = or_suspect_bits<MODE>(suspect, w0, w1, c[k]);
     }
     const uint32_t col = ModeTraits<MODE>::masks_column ? (c[k] & 0x00FFFFFFu) : c[k];
-    // A column no check caught can point outside vec[] (the reference reads out of bounds: UB): the
-    // gather address is clamped.  Mode none also drops the product, as the oracle does; in the checked
-    // modes an out-of-range column either trips `suspect` (constraints) or belongs to a multi-bit fault
-    // the code cannot see at all, so the fast walk does not spend a compare on it.
-    ok[k] = ((uint32_t)k < count) && (MODE != ABFT_MODE_NONE || col < n_cols);
+    // A column no check caught (mode none, or a multi-bit fault the code cannot see) can point outside
+    // vec[]: the reference reads out of bounds there (UB); here, and in the oracle, the column is clamped
+    // to the last entry.
+    ok[k] = ((uint32_t)k < count);
     xv[k] = __ldg(x + min(col, n_cols - 1u));
   }
 #pragma unroll

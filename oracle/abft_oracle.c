@@ -371,8 +371,9 @@ int orc_spmv(orc_matrix *m, const double *vec, double *result, orc_event *log, i
        * Deviation: a corrupted column that no check caught (mode none, a
        * mis-corrected multi-bit fault, the unchecked modes' index flips) makes
        * the reference read vec[] out of bounds (undefined behaviour); the
-       * oracle and the CUDA target both take the missing entry as 0. */
-      double xv = (col < m->N) ? vec[col] : 0.0;
+       * oracle and the CUDA target both read the LAST entry of vec[] instead
+       * (the column is clamped to N-1). */
+      double xv = vec[col < m->N ? col : m->N - 1];
       double prod = m->values[i] * xv;
       tmp = tmp + prod;
     }

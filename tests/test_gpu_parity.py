@@ -302,14 +302,10 @@ def test_all_96_single_flips(pkg, O, mode):
             assert (fatal, events) == (fatal0, ev0), (index, bit)
             cols, _, vals = ctx.read_matrix(A)
             assert np.array_equal(cols, om.cols) and np.array_equal(vals.view(np.uint64), om.values.view(np.uint64))
-            if not fatal and mode != "none":
-                assert np.array_equal(y, y0), (index, bit)
-            if not fatal and mode == "none":
-                # an index flip can leave the matrix: the reference reads out of bounds there (UB);
-                # the CUDA target treats the missing vector entry as 0
-                col = int(om.cols[index])
-                if col < t.N:
-                    assert np.array_equal(y, y0)
+            if not fatal:
+                # (an undetected index flip can point outside vec[]: the reference reads out of bounds there,
+                # oracle and CUDA target both clamp the column to the last entry)
+                assert np.array_equal(y, y0, equal_nan=True), (index, bit)
             # a second spmv finds nothing new in the correcting modes
             if mode in ("sec7", "sec8", "secded"):
                 v, w = ctx.create_vector(t.N), ctx.create_vector(t.N)
@@ -497,10 +493,15 @@ def test_all_double_flips_match_oracle(pkg, O, mode):
         for i, (a, b) in enumerate(batch):
             for bit in (a, b):
                 ctx.flip_bit(A, i, bit); om.flip(i, bit)
-        y, fatal, events, _ = gpu_spmv(ctx, A, np.ones(n))
+        v, w = ctx.create_vector(n), ctx.create_vector(n)
+        ctx.upload(v, np.ones(n))
+        ctx.spmv(A, v, w)
+        events, fatal = ctx.poll_events(cap=2048)
+        y = ctx.download(w)
         y0, fatal0, ev0 = om.spmv(np.ones(n))
-        assert (fatal, events) == (fatal0, ev0)
+        assert fatal == fatal0 and len(events) == len(ev0)
+        assert events == ev0
         cols, _, vals = ctx.read_matrix(A)
         assert np.array_equal(cols, om.cols) and np.array_equal(vals.view(np.uint64), om.values.view(np.uint64))
-        assert np.array_equal(y.view(np.uint64), y0.view(np.uint64))
+        assert np.array_equal(y, y0, equal_nan=True)      # (a flipped exponent can make a NaN: payloads may differ)
         ctx.close()
