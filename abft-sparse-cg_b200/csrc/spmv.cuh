@@ -158,22 +158,8 @@ __device__ __forceinline__ uint32_t element_suspect(uint32_t w0, uint32_t w1, ui
   return 0;
 }
 
-// like element_suspect but without the final `& 1`: callers OR these over a whole row and
-// test bit 0 once
-template <int MODE>
-__device__ __forceinline__ uint32_t element_suspect_bits(uint32_t w0, uint32_t w1, uint32_t col) {
-  if (MODE == ABFT_MODE_SED || MODE == ABFT_MODE_SEC8) return __popc(w0 ^ w1 ^ col);
-  if (MODE == ABFT_MODE_SEC7 || MODE == ABFT_MODE_SECDED) {
-    uint32_t a = __popc(masked<1>(w0, w1, col)) | __popc(masked<2>(w0, w1, col)) | __popc(masked<3>(w0, w1, col));
-    uint32_t b = __popc(masked<4>(w0, w1, col)) | __popc(masked<5>(w0, w1, col)) | __popc(masked<6>(w0, w1, col));
-    uint32_t c = a | b | __popc(masked<7>(w0, w1, col));
-    if (MODE == ABFT_MODE_SECDED) c |= __popc(w0 ^ w1 ^ col);
-    return c;
-  }
-  return 0;
-}
-
-// acc | (verdict bits of one element), written as a flat chain of 3-input ORs (one LOP3 each)
+// acc | (verdict bits of one element), without the final `& 1`: callers OR these over a whole row and test
+// bit 0 once.  Written as a flat chain of 3-input ORs (one LOP3 each).
 template <int MODE>
 __device__ __forceinline__ uint32_t or_suspect_bits(uint32_t acc, uint32_t w0, uint32_t w1, uint32_t col) {
   if (MODE == ABFT_MODE_SED || MODE == ABFT_MODE_SEC8) return acc | __popc(w0 ^ w1 ^ col);
@@ -221,10 +207,10 @@ __device__ __forceinline__ double element_product(uint32_t cw, double v, uint32_
 // are added to `sum` in element order.  No per-element branch: the checks only OR their verdict
 // into `suspect`; the caller re-walks the row on the careful path if bit 0 ends up set (rare).
 // Slots past the row's end (k >= count) are still loaded and checked -- they hold the next row's
-// elements, stale elements of an earlier tile, or the zeros the buffers start with, i.e. valid code
-// words (the stage is filled kOverrun elements past the tile's end for exactly this), and at worst
-// a false `suspect` sends the row down the (exact) careful path -- but they are never added.  That
-// keeps the loop body free of selects and zero-fills.
+// elements (the stage is filled kOverrun elements past the tile's end for exactly this; the buffers start
+// zeroed and the matrix arrays end in zero padding), i.e. valid code words; at worst a faulty neighbour
+// raises a false `suspect` and sends this row down the (exact) careful path -- but they are never added.
+// That keeps the loop body free of selects and zero-fills.
 template <int MODE, int LEN>
 __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_t count, const uint32_t *s_cols,
                                              const double *s_vals, uint32_t n_cols, const double *__restrict__ x,

@@ -149,9 +149,33 @@ def alg_bytes(N, nnz):
 def cpu_reference_run(args, t, b, iters, warm):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
-    kind = "reference" if os.path.exists(O.REF_SO) else None
-    if kind is None:
-        raise RuntimeError("oracle/_ref/libref_csr.so missing (built here from /root/reference by oracle/Makefile)")
+    if not os.path.exists(O.REF_SO):
+        # oracle/_ref (the reference built from its own sources) did not travel: fall back to the oracle's C port
+        # of the same algorithm -- serial, so it understates what the reference's OpenMP spmv would do
+        mode = args.mode
+        t0 = time.time()
+        om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+        t_create = time.time() - t0
+        L = O.lib()
+        N = t.N
+        x = np.zeros(N); r = b.copy(); p = b.copy(); w = np.zeros(N)
+        rr = L.orc_dot(r, r, N)
+
+        def run(k):
+            nonlocal rr
+            for _ in range(k):
+                y, fatal, ev = om.spmv(p)
+                w[:] = y
+                pw = L.orc_dot(p, w, N)
+                rr_new = L.orc_calc_xr(x, r, p, w, rr / pw, N)
+                L.orc_calc_p(p, r, rr_new / rr, N)
+                rr = rr_new
+        run(min(warm, 1))
+        t0 = time.time()
+        run(iters)
+        dt = time.time() - t0
+        return iters / dt, dt, t_create, "port"
+    kind = "reference"
     rc = O.RefContext(args.mode if args.mode != "crc32c" else "secded")
     t0 = time.time()
     rc.create_matrix(t.cols, t.rows, t.vals, t.N)
@@ -215,7 +239,7 @@ def main():
         t = slab_triplets(mg, n, 0, N) if full is None else full
         b = np.random.default_rng(1).random(N)
         its, dt, t_create, kind = cpu_reference_run(args, t, b, args.steps, args.warmup)
-        cores = os.cpu_count()
+        cores = os.cpu_count() if kind == "reference" else 1
         line = {"impl": "reference", "metric": "cg_iterations_per_sec", "value": its, "unit": "it/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / its, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -482,7 +506,8 @@ def main():
         if not args.no_cpu_baseline:
             try:
                 v, dt, t_create, kind = cpu_reference_run(args, t, b_full, args.cpu_iters, 1)
-                line["cpu_baseline"] = {"value": v, "unit": "it/s", "cores": os.cpu_count(), "kind": kind,
+                line["cpu_baseline"] = {"value": v, "unit": "it/s", "cores": os.cpu_count() if kind == "reference" else 1,
+                                        "kind": kind,
                                         "sample": f"{args.cpu_iters} CG iterations on the full matrix "
                                                   f"({dt:.1f} s; create_matrix {t_create:.1f} s untimed), OpenMP all cores"}
             except Exception as e:
