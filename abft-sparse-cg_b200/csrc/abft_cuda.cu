@@ -309,6 +309,21 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
   abft_matrix *m = new abft_matrix();
   const size_t nz = (size_t)std::max(nnz, 1);
   uint32_t *d_coo_rows = nullptr;
+  // every early `return nullptr` below releases what was allocated so far
+  struct Cleanup {
+    abft_matrix *&m;
+    uint32_t *&tmp;
+    bool armed = true;
+    ~Cleanup() {
+      if (!armed) return;
+      cudaFree(tmp);
+      cudaFree(m->view.cols);
+      cudaFree(m->view.values);
+      cudaFree(m->d_rowptr);
+      cudaFree(m->d_tiles);
+      delete m;
+    }
+  } cleanup{m, d_coo_rows};
   // +16 elements of padding: the TMA bulk copies of a tile round its window out to 16-byte granules
   CKP(cudaMalloc(&m->view.cols, sizeof(uint32_t) * (nz + 16)));
   CKP(cudaMalloc(&m->view.values, sizeof(double) * (nz + 16)));
@@ -340,6 +355,7 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
                       c->stream));
   CKP(cudaStreamSynchronize(c->stream));
   CKP(cudaFree(d_coo_rows));
+  d_coo_rows = nullptr;
   std::vector<Tile> tiles;
   build_tiles(h_rowptr.data(), (uint32_t)n_rows, tiles);
   m->n_tiles = (int)tiles.size();
@@ -359,6 +375,7 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
   m->view.row_offset = (uint32_t)row_offset;
   m->view.nnz_offset = (uint32_t)nnz_offset;
   m->nnz_offset = nnz_offset;
+  cleanup.armed = false;
   return m;
 }
 
