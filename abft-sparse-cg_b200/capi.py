@@ -23,7 +23,7 @@ SYMBOLS = [
     "abft_cuda_ctx_stream",
     "abft_cuda_matrix_create", "abft_cuda_matrix_create_part", "abft_cuda_matrix_destroy",
     "abft_cuda_matrix_rows", "abft_cuda_matrix_nnz", "abft_cuda_matrix_read", "abft_cuda_matrix_poke_rowptr",
-    "abft_cuda_matrix_poke_col",
+    "abft_cuda_matrix_poke_col", "abft_cuda_matrix_poke_value",
     "abft_cuda_vector_create", "abft_cuda_vector_wrap", "abft_cuda_vector_view", "abft_cuda_vector_destroy",
     "abft_cuda_vector_len", "abft_cuda_vector_dev_ptr", "abft_cuda_vector_map", "abft_cuda_vector_unmap",
     "abft_cuda_vector_copy",
@@ -89,6 +89,7 @@ def load():
     sig("abft_cuda_matrix_read", i32, vp, vp, vp, vp, vp)
     sig("abft_cuda_matrix_poke_rowptr", i32, vp, vp, i32, u32)
     sig("abft_cuda_matrix_poke_col", i32, vp, vp, i32, u32)
+    sig("abft_cuda_matrix_poke_value", i32, vp, vp, i32, f64)
     sig("abft_cuda_vector_create", vp, vp, i32)
     sig("abft_cuda_vector_wrap", vp, vp, vp, i32)
     sig("abft_cuda_vector_view", vp, vp, vp, i32, i32)

@@ -434,6 +434,22 @@ int abft_cuda_matrix_poke_col(abft_ctx *c, abft_matrix *m, int index, uint32_t v
   return 0;
 }
 
+int abft_cuda_matrix_poke_value(abft_ctx *c, abft_matrix *m, int index, double value) {
+  REQUIRE(c && m, "null argument");
+  REQUIRE(index >= 0 && (uint32_t)index < m->view.nnz, "index out of range");
+  CK(cudaSetDevice(c->device));
+  // two 4-byte stores through the same tiny kernel (keeps everything on the context's stream)
+  uint32_t w[2];
+  memcpy(w, &value, 8);
+  uint32_t *words = reinterpret_cast<uint32_t *>(m->view.values + index);
+  poke_u32_kernel<<<1, 1, 0, c->stream>>>(words, w[0]);
+  poke_u32_kernel<<<1, 1, 0, c->stream>>>(words + 1, w[1]);
+  c->launches += 2;
+  c->epoch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int abft_cuda_flip_bit(abft_ctx *c, abft_matrix *m, int64_t index, int bit) {
   REQUIRE(c && m, "null argument");
   REQUIRE(bit >= 0 && bit < 96, "bit out of range");

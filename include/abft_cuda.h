@@ -112,6 +112,7 @@ int abft_cuda_matrix_read(abft_ctx *ctx, const abft_matrix *mat, uint32_t *cols_
 /* overwrite one row pointer (fault injection into rows[] for the CONSTRAINTS checks) */
 int abft_cuda_matrix_poke_rowptr(abft_ctx *ctx, abft_matrix *mat, int row, uint32_t value);
 int abft_cuda_matrix_poke_col(abft_ctx *ctx, abft_matrix *mat, int index, uint32_t value);
+int abft_cuda_matrix_poke_value(abft_ctx *ctx, abft_matrix *mat, int index, double value);
 
 /* ---- vectors (CSR/CPUContext.cpp:54-80) ---- */
 abft_vector *abft_cuda_vector_create(abft_ctx *ctx, int N); /* zero-filled */
