@@ -62,6 +62,7 @@ struct abft_matrix {
   MatView view{};
   uint32_t *d_rowptr = nullptr;
   Tile *d_tiles = nullptr;
+  unsigned int *d_tile_counter = nullptr;  // dynamic spmv schedule (matrices with irregular tiles)
   int n_tiles = 0;
   int64_t nnz_offset = 0;
 };
@@ -321,6 +322,7 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
       cudaFree(m->view.values);
       cudaFree(m->d_rowptr);
       cudaFree(m->d_tiles);
+      cudaFree(m->d_tile_counter);
       delete m;
     }
   } cleanup{m, d_coo_rows};
@@ -363,11 +365,20 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
     fail(-1, "matrix needs more spmv tiles than the reduction buffer holds", __FILE__, __LINE__);
     return nullptr;
   }
+  // irregular tiles cost very different amounts (and the gathers make even equal tiles take 0.3x .. 2x the mean):
+  // such a matrix is scheduled dynamically, CTAs drawing tiles from a counter (spmv.cuh)
+  bool irregular = false;
+  for (const Tile &t : tiles) irregular |= !(t.info & kTileRegular);
+  if (irregular && c->mode != ABFT_MODE_CRC32C) {
+    CKP(cudaMalloc(&m->d_tile_counter, sizeof(unsigned int)));
+    CKP(cudaMemset(m->d_tile_counter, 0, sizeof(unsigned int)));
+  }
   CKP(cudaMalloc(&m->d_tiles, sizeof(Tile) * (size_t)std::max(m->n_tiles, 1)));
   if (m->n_tiles)
     CKP(cudaMemcpy(m->d_tiles, tiles.data(), sizeof(Tile) * (size_t)m->n_tiles, cudaMemcpyHostToDevice));
   m->view.rowptr = m->d_rowptr;
   m->view.tiles = m->d_tiles;
+  m->view.tile_counter = m->d_tile_counter;
   m->view.n_tiles = (uint32_t)m->n_tiles;
   m->view.n_rows = (uint32_t)n_rows;
   m->view.nnz = (uint32_t)nnz;
@@ -394,6 +405,7 @@ void abft_cuda_matrix_destroy(abft_ctx *c, abft_matrix *m) {
   cudaFree(m->view.values);
   cudaFree(m->d_rowptr);
   cudaFree(m->d_tiles);
+  cudaFree(m->d_tile_counter);
   delete m;
 }
 

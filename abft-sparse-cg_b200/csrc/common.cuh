@@ -131,19 +131,22 @@ struct ReduceOut {
 
 // Every CTA contributes `mine` (valid in thread 0); the CTA that arrives last
 // adds the partials in index order with a fixed tree and publishes the value.
-__device__ __forceinline__ void grid_sum_finalize(double mine, const ReduceOut &o, double *s_warp) {
+// n_given != 0: the CTAs have already stored o.partials[0 .. n_given) themselves (spmv's per-tile partials) and
+// `mine` is ignored.  Returns true in every thread of the CTA that did the final sum.
+__device__ __forceinline__ bool grid_sum_finalize(double mine, const ReduceOut &o, double *s_warp, unsigned int n_given = 0) {
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
-    o.partials[blockIdx.x] = mine;
+    if (n_given == 0) o.partials[blockIdx.x] = mine;
     __threadfence();
     unsigned int t = atomicAdd(o.counter, 1u);
     s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) return false;
   __threadfence();
   double acc = 0.0;
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) acc += __ldcg(o.partials + i);
+  const unsigned int n_partials = n_given ? n_given : gridDim.x;
+  for (unsigned int i = threadIdx.x; i < n_partials; i += kBlock) acc += __ldcg(o.partials + i);
   double total = block_sum(acc, s_warp);
   if (threadIdx.x == 0) {
     if (o.peers.world > 1) total = peer_allreduce(total, o.peers);
@@ -157,6 +160,7 @@ __device__ __forceinline__ void grid_sum_finalize(double mine, const ReduceOut &
     *o.counter = 0u;
     __threadfence_system();
   }
+  return true;
 }
 
 }  // namespace abft

@@ -35,8 +35,14 @@ constexpr int kTileNnz = 2048;
 constexpr int kTileRows = kBlock;  // 256: one row per thread
 constexpr int kStages = 2;
 constexpr uint32_t kSeqRowMax = 32;  // irregular tiles: rows up to this long are summed sequentially by one thread
+#ifndef ABFT_ELEM_BATCH
+#define ABFT_ELEM_BATCH 1  // measured on the power-law workload: 1 -> 0.50 ms, 2 -> 0.52, 4 -> 0.53, 8 -> 0.60 (gather-rate bound)
+#endif
+constexpr int kLongBatch = 4;  // rows longer than a tile: elements each thread streams at a time
+constexpr int kElemBatch = ABFT_ELEM_BATCH;          // irregular tiles: gathers each thread keeps in flight in the element phase
 constexpr uint32_t kOverrun = 8;  // elements staged past a tile's end (>= longest unrolled walk - 1)
 
+constexpr uint32_t kTileNone = 0xFFFFFFFFu;   // info of the "no more tiles" marker
 constexpr uint32_t kTileRegular = 1u << 16;  // info flag: thread-per-row path
 constexpr uint32_t kTileLongRow = 1u << 17;  // info flag: single row > kTileNnz, streamed
 constexpr int kTileMaxLenShift = 18;         // info bits 18..29: longest row of the tile
@@ -53,6 +59,7 @@ struct MatView {
   uint32_t *cols;          // [nnz (+pad)] column word incl. check bits
   double *values;          // [nnz (+pad)]
   const Tile *tiles;
+  unsigned int *tile_counter;  // dynamic schedule (matrices with irregular tiles): next tile to hand out; null: tile b, b+grid, ...
   uint32_t n_tiles;
   uint32_t n_rows, nnz;
   uint32_t n_cols;      // global N: bound for the gather
@@ -78,6 +85,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
@@ -202,6 +212,35 @@ __device__ __forceinline__ double element_product(uint32_t cw, double v, uint32_
   return __dmul_rn(v, xv);
 }
 
+// U elements at once (element-parallel paths): all checks and gathers first (U independent loads in flight),
+// then the products.  The checks only OR their verdict into one word; a batch that trips goes through
+// element_product one element at a time (rare).  Slots with ok[k] == false must still hold a valid element
+// (callers repeat their first one): they are checked and gathered, never repaired, and return garbage.
+template <int MODE, int U>
+__device__ __forceinline__ void batch_products(const uint32_t (&li)[U], const uint32_t (&cw)[U], const double (&v)[U],
+                                               const bool (&ok)[U], const MatView &A, const double *__restrict__ x,
+                                               const LogRef &L, double (&out)[U]) {
+  double xv[U];
+  uint32_t suspect = 0;
+#pragma unroll
+  for (int k = 0; k < U; k++) {
+    if (ModeTraits<MODE>::per_element_ecc) {
+      uint32_t w0, w1;
+      split_value(v[k], w0, w1);
+      suspect = or_suspect_bits<MODE>(suspect, w0, w1, cw[k]);
+    }
+    uint32_t col = ModeTraits<MODE>::masks_column ? (cw[k] & 0x00FFFFFFu) : cw[k];
+    xv[k] = __ldg(x + min(col, A.n_cols - 1u));
+  }
+  if (!(suspect & 1u)) {
+#pragma unroll
+    for (int k = 0; k < U; k++) out[k] = __dmul_rn(v[k], xv[k]);
+  } else {
+    for (int k = 0; k < U; k++)
+      if (ok[k]) out[k] = element_product<MODE>(cw[k], v[k], li[k], A, x, L);
+  }
+}
+
 // Fast walk over up to LEN consecutive elements of one row, fully unrolled: all shared-memory
 // loads first, then all checks and gathers (LEN independent loads in flight), then the products
 // are added to `sum` in element order.  No per-element branch: the checks only OR their verdict
@@ -292,6 +331,8 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   StageBuf *stage = reinterpret_cast<StageBuf *>(dyn_smem);
   __shared__ __align__(8) uint64_t s_full[kStages];
   __shared__ Tile s_tile[kStages];
+  __shared__ uint32_t s_tidx[kStages];              // index of the staged tile (dynamic schedule: its partial's slot)
+  __shared__ double s_wdot[2][kBlock / 32];         // dynamic schedule: the warps' dot() partials of a tile
   __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? 1024 : 1];
   __shared__ double s_warp[kBlock / 32];
 
@@ -299,7 +340,20 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
 
   const int tid = threadIdx.x;
   const uint32_t G = gridDim.x;
-  const uint32_t n_my = (A.n_tiles > blockIdx.x) ? (A.n_tiles - blockIdx.x + G - 1) / G : 0;
+  // Tile source.  Static: CTA b takes tiles b, b+grid, ... (the whole chip sweeps the matrix as one front; each
+  // thread keeps its own dot() partial).  Dynamic (matrices with irregular tiles, whose cost per tile varies by
+  // 5x): CTAs draw tiles from a counter; a tile's dot() contribution is then reduced per tile into
+  // red.partials[tile], so the value published at the end is the same whichever CTA ran which tile.
+  const bool dynamic = A.tile_counter != nullptr;
+  __shared__ uint32_t s_next_static;  // (only thread 0 uses it: shared memory instead of a register in every thread)
+  Tile ahead{};                       // thread 0: descriptor and index of the next tile to issue
+  uint32_t ahead_idx = 0;
+  auto fetch_ahead = [&]() {
+    if (dynamic) ahead_idx = atomicAdd(A.tile_counter, 1u);
+    else { ahead_idx = s_next_static; s_next_static = ahead_idx + G; }
+    if (ahead_idx < A.n_tiles) ahead = A.tiles[ahead_idx];  // consumed an iteration later: the latency overlaps a tile's work
+    else ahead.info = kTileNone;
+  };
 
   {
     // the row walk may look a few slots past the data TMA delivers: start from all-zero buffers
@@ -341,14 +395,16 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     }
   };
 
-  Tile ahead{};  // descriptor of the next tile to issue (thread 0 only)
   if (tid == 0) {
-    for (uint32_t j = 0; j + 1 < (uint32_t)kStages && j < n_my; j++) {
-      const Tile t = A.tiles[blockIdx.x + j * G];
-      s_tile[j] = t;
-      issue((int)j, t);
+    s_next_static = blockIdx.x;
+    for (int j = 0; j + 1 < kStages; j++) {
+      fetch_ahead();
+      s_tile[j] = ahead;
+      s_tidx[j] = ahead_idx;
+      if (ahead.info != kTileNone) issue(j, ahead);
+      else mbar_arrive(&s_full[j]);  // nothing to stream: complete the phase so the waiters get to see the marker
     }
-    if ((uint32_t)(kStages - 1) < n_my) ahead = A.tiles[blockIdx.x + (kStages - 1) * G];
+    fetch_ahead();
   }
   if (wait.mask) {
     // the matrix stream of the first tile is already in flight; vec[] is only touched after this
@@ -364,20 +420,35 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
 
   double dot_part = 0.0;
 
-  for (uint32_t it = 0; it < n_my; it++) {
+  uint32_t it = 0;
+  for (;; it++) {
     const int st = (int)(it % kStages);
-    // refill the stage the previous iteration released
+    // thread 0: bank the previous tile's dot() partial (dynamic schedule), refill the stage that tile released
     if (tid == 0) {
-      const uint32_t j = it + kStages - 1;
-      if (j < n_my) {
-        s_tile[j % kStages] = ahead;
-        issue((int)(j % kStages), ahead);
-        if (j + 1 < n_my) ahead = A.tiles[blockIdx.x + (j + 1) * G];  // latency overlaps this tile's work
+      if (dynamic && it > 0) {
+        // the warps' sums, added in warp order
+        const double *wd = s_wdot[(it - 1) & 1u];
+        double tp = wd[0];
+#pragma unroll
+        for (int k = 1; k < kBlock / 32; k++) tp = __dadd_rn(tp, wd[k]);
+        red.partials[s_tidx[(it - 1) % kStages]] = tp;
+      }
+      const int js = (int)((it + kStages - 1) % kStages);
+      s_tile[js] = ahead;
+      s_tidx[js] = ahead_idx;
+      if (ahead.info != kTileNone) {
+        issue(js, ahead);
+        fetch_ahead();
+      } else {
+        mbar_arrive(&s_full[js]);  // nothing to stream: complete the phase so the waiters get to see the marker
       }
     }
     mbar_wait(&s_full[st], (it / kStages) & 1u);
-    const Tile t = s_tile[st];
+    const Tile t = s_tile[st];  // (written by thread 0 before it armed the barrier)
+    if (t.info == kTileNone) break;
+    const bool irregular_tile = !(t.info & (kTileLongRow | kTileRegular)) && MODE != ABFT_MODE_CRC32C;
     const StageBuf &B = stage[st];
+    if (dynamic) dot_part = 0.0;  // reduced per tile below
     const uint32_t nrows = t.info & 0xFFFFu;
     const uint32_t n = t.nnz_end - t.nnz_begin;
     const uint32_t rb = t.row_begin & ~3u, cb = t.nnz_begin & ~3u, vb = t.nnz_begin & ~1u;
@@ -388,18 +459,29 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
       // ---------------- one long row: stream it from global memory in chunks ----------------
       double acc = 0.0;
       bool flagged = false;
-      for (uint32_t base = 0; base < n; base += kBlock) {
-        const uint32_t e = base + tid;
-        if (e < n) {
-          const uint32_t i = t.nnz_begin + e;
-          const uint32_t cw = ld_stream(A.cols + i);
-          const double val = ld_stream(A.values + i);
-          if (MODE == ABFT_MODE_CONSTRAINTS && !flagged) {
-            if (cw >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + t.row_begin); flagged = true; }
-            else if (e + 1 < n && A.cols[i + 1] <= cw) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + t.row_begin); flagged = true; }
-          }
-          acc = __dadd_rn(acc, element_product<MODE>(cw, val, i, A, x, L));
+      for (uint32_t base = tid; base < n; base += kLongBatch * kBlock) {
+        uint32_t li[kLongBatch], cw[kLongBatch];
+        double val[kLongBatch], pr[kLongBatch];
+        bool ok[kLongBatch];
+#pragma unroll
+        for (int k = 0; k < kLongBatch; k++) {
+          ok[k] = (k == 0) || (base + k * kBlock < n);
+          li[k] = t.nnz_begin + (ok[k] ? base + k * kBlock : base);
+          cw[k] = ld_stream(A.cols + li[k]);
+          val[k] = ld_stream(A.values + li[k]);
         }
+        if (MODE == ABFT_MODE_CONSTRAINTS && !flagged) {
+#pragma unroll
+          for (int k = 0; k < kLongBatch; k++)
+            if (ok[k] && !flagged) {
+              if (cw[k] >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + li[k], A.row_offset + t.row_begin); flagged = true; }
+              else if (li[k] + 1 < t.nnz_end && A.cols[li[k] + 1] <= cw[k]) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + li[k], A.row_offset + t.row_begin); flagged = true; }
+            }
+        }
+        batch_products<MODE, kLongBatch>(li, cw, val, ok, A, x, L, pr);
+#pragma unroll
+        for (int k = 0; k < kLongBatch; k++)
+          if (ok[k]) acc = __dadd_rn(acc, pr[k]);
       }
       if (MODE == ABFT_MODE_CRC32C && tid == 0) {
         // long rows are rare: one thread walks the row for the CRC
@@ -422,7 +504,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         dot_part = __dadd_rn(dot_part, __dmul_rn(total, x[A.row_offset + t.row_begin]));
       }
     } else {
-      const bool irregular = !(t.info & kTileRegular) && MODE != ABFT_MODE_CRC32C;
+      const bool irregular = irregular_tile;
       // CONSTRAINTS, one row, exactly the reference's checks in the reference's order
       // (CSR/CPUContext.cpp:173-182 row checks, :184-203 element checks); returns the row sum
       auto constraints_careful = [&](uint32_t grow, uint32_t rs, uint32_t re) -> double {
@@ -448,19 +530,105 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         return sum;
       };
       if (irregular) {
-        // ---------------- irregular tile, element phase: product -> shared memory (in place) ----------------
+        // ---------------- irregular tile ----------------
+        // The tile's rows are dealt to the warps in equal runs of consecutive rows (warp w owns rows
+        // [w*c, (w+1)*c), c = ceil(nrows / 8) <= 32, one per lane), so every warp has its share whatever the tile's
+        // row count, and a warp finishes its own rows -- short and long -- without a CTA-wide barrier.  The dot()
+        // operand is fetched now, ahead of the element phase.
+        const int lane = tid & 31, warp = tid >> 5;
+        const uint32_t per_warp = (nrows + kBlock / 32 - 1) / (kBlock / 32);
+        const uint32_t q = (uint32_t)warp * per_warp + lane;
+        const bool has_q = (uint32_t)lane < per_warp && q < nrows;
+        const uint32_t qrow = t.row_begin + q;
+        const double xq = has_q ? x[A.row_offset + qrow] : 0.0;
+
+        // element phase: product -> shared memory (in place).  kElemBatch elements per thread at a time: all
+        // shared-memory loads, then all checks and gathers, then the stores.  The checks only OR their verdict
+        // into `suspect`; a batch that trips goes through element_product one element at a time (rare).
         double *prod = const_cast<double *>(B.vals);
-        for (uint32_t e = tid; e < n; e += kBlock) {
-          const uint32_t li = t.nnz_begin + e;
-          prod[li - vb] = element_product<MODE>(B.cols[li - cb], B.vals[li - vb], li, A, x, L);
+        for (uint32_t e0 = tid; e0 < n; e0 += kElemBatch * kBlock) {
+          uint32_t li[kElemBatch], cw[kElemBatch];
+          double v[kElemBatch], pr[kElemBatch];
+          bool ok[kElemBatch];
+#pragma unroll
+          for (int k = 0; k < kElemBatch; k++) {
+            // slots past the tile's end repeat this thread's first element (loaded, checked, never stored)
+            ok[k] = (k == 0) || (e0 + k * kBlock < n);
+            li[k] = t.nnz_begin + (ok[k] ? e0 + k * kBlock : e0);
+            cw[k] = B.cols[li[k] - cb];
+            v[k] = B.vals[li[k] - vb];
+          }
+          batch_products<MODE, kElemBatch>(li, cw, v, ok, A, x, L, pr);
+#pragma unroll
+          for (int k = 0; k < kElemBatch; k++)
+            if (ok[k]) prod[li[k] - vb] = pr[k];
         }
         __syncthreads();
-      }
-      if (has_row) {
+
+        // row phase: a thread adds its row's products in element order (the reference's order: same bits) if
+        // the row has at most kSeqRowMax elements ...
+        uint32_t rs = 0, re = 0;
+        if (has_q) {
+          rs = B.rptr[qrow - rb];
+          re = B.rptr[qrow + 1 - rb];
+          if (MODE != ABFT_MODE_CONSTRAINTS) {
+            // these modes trust rows[] like the reference; clamp so a bad pointer cannot fault
+            rs = min(max(rs, t.nnz_begin), t.nnz_end);
+            re = min(max(re, rs), t.nnz_end);
+          }
+        }
+        // (CONSTRAINTS: a corrupted rows[] can send the row outside the staged window; then the careful path
+        // that mirrors the reference's checks one by one)
+        const bool in_window = rs >= t.nnz_begin && re <= t.nnz_end && rs <= re;
+        const bool is_long = has_q && in_window && (re - rs > kSeqRowMax);
+        double sum = 0.0;
+        if (has_q && !is_long) {
+          if (MODE == ABFT_MODE_CONSTRAINTS) {
+            bool bad = !in_window;
+            if (!bad)
+              for (uint32_t i = rs; i < re; i++) {
+                const uint32_t col = B.cols[i - cb];
+                bad |= (col >= A.n_cols);
+                if (i + 1 < re) bad |= (B.cols[i + 1 - cb] <= col);
+                sum = __dadd_rn(sum, B.vals[i - vb]);
+              }
+            if (bad) sum = constraints_careful(qrow, rs, re);
+          } else {
+#pragma unroll 4
+            for (uint32_t i = rs; i < re; i++) sum = __dadd_rn(sum, B.vals[i - vb]);
+          }
+        }
+        // ... and the warp then takes its lanes' longer rows one at a time: lane-strided partial sums + a fixed
+        // shuffle tree (deterministic; not the sequential order, so not bit-identical to the CPU sum)
+        uint32_t longs = __ballot_sync(0xffffffffu, is_long);
+        while (longs) {
+          const int src = __ffs(longs) - 1;
+          longs &= longs - 1;
+          const uint32_t ls = __shfl_sync(0xffffffffu, rs, src), le = __shfl_sync(0xffffffffu, re, src);
+          double part = 0.0;
+          bool bad = false;
+          for (uint32_t i = ls + lane; i < le; i += 32) {
+            if (MODE == ABFT_MODE_CONSTRAINTS) {
+              // CSR/CPUContext.cpp:188-200; a violation sends the whole row down the careful path
+              const uint32_t c = B.cols[i - cb];
+              bad |= (c >= A.n_cols);
+              if (i + 1 < le) bad |= (B.cols[i + 1 - cb] <= c);
+            }
+            part = __dadd_rn(part, B.vals[i - vb]);
+          }
+          part = warp_sum(part);
+          part = __shfl_sync(0xffffffffu, part, 0);
+          const bool any_bad = (MODE == ABFT_MODE_CONSTRAINTS) && __any_sync(0xffffffffu, bad);
+          if (lane == src) sum = any_bad ? constraints_careful(qrow, rs, re) : part;
+        }
+        if (has_q) {
+          y[qrow] = sum;
+          dot_part = __dadd_rn(dot_part, __dmul_rn(sum, xq));
+        }
+      } else if (has_row) {
         uint32_t rs = B.rptr[row - rb], re = B.rptr[row + 1 - rb];
         double sum = 0.0;
         bool careful = true;
-        bool long_row = false;  // irregular tile: left to the warp-per-row pass
         if (MODE != ABFT_MODE_CONSTRAINTS) {
           // these modes trust rows[] like the reference; clamp so a bad pointer cannot fault
           rs = min(max(rs, t.nnz_begin), t.nnz_end);
@@ -469,7 +637,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         // ---------------- regular tile: thread-per-row straight from the staged stream ----------------
         // (CONSTRAINTS only if its row pointers keep the row inside the staged window; anything else,
         // i.e. a corrupted rows[], takes the careful path that mirrors the reference's checks one by one)
-        if ((t.info & kTileRegular) && MODE != ABFT_MODE_CRC32C &&
+        if (MODE != ABFT_MODE_CRC32C &&
             (MODE != ABFT_MODE_CONSTRAINTS || (rs >= t.nnz_begin && re <= t.nnz_end && rs <= re))) {
           const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the CTA
           const uint32_t len = re - rs;
@@ -489,21 +657,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         }
         if (careful) {
           sum = 0.0;
-          if (MODE == ABFT_MODE_CONSTRAINTS && irregular && rs >= t.nnz_begin && re <= t.nnz_end && rs <= re) {
-            // irregular tile: products are staged; check the columns while adding them up
-            if (re - rs <= kSeqRowMax) {
-              bool bad = false;
-              for (uint32_t i = rs; i < re; i++) {
-                const uint32_t col = B.cols[i - cb];
-                bad |= (col >= A.n_cols);
-                if (i + 1 < re) bad |= (B.cols[i + 1 - cb] <= col);
-                sum = __dadd_rn(sum, B.vals[i - vb]);
-              }
-              if (bad) sum = constraints_careful(row, rs, re);
-            } else {
-              long_row = true;
-            }
-          } else if (MODE == ABFT_MODE_CONSTRAINTS) {
+          if (MODE == ABFT_MODE_CONSTRAINTS) {
             sum = constraints_careful(row, rs, re);
           } else if (MODE == ABFT_MODE_CRC32C) {
             const uint32_t len = re - rs;
@@ -527,64 +681,35 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
             }
             if (len >= 4 && (crc ^ 0xFFFFFFFFu) != stored) bad = true;
             if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
-          } else if (t.info & kTileRegular) {
+          } else {
             // element by element, repairing / reporting as the mode demands (the owning thread
             // writes a corrected element back)
             for (uint32_t i = rs; i < re; i++)
               sum = __dadd_rn(sum, element_product<MODE>(B.cols[i - cb], B.vals[i - vb], i, A, x, L));
-          } else {
-            // ---------------- irregular tile, row phase (short rows): add the products in element order ----------------
-            // (rows longer than kSeqRowMax are left to the warp-per-row pass below)
-            if (re - rs <= kSeqRowMax) {
-#pragma unroll 4
-              for (uint32_t i = rs; i < re; i++) sum = __dadd_rn(sum, B.vals[i - vb]);
-            } else {
-              long_row = true;
-            }
           }
         }
-        if (!long_row) {
-          y[row] = sum;
-          dot_part = __dadd_rn(dot_part, __dmul_rn(sum, x[A.row_offset + row]));
-        }
+        y[row] = sum;
+        dot_part = __dadd_rn(dot_part, __dmul_rn(sum, x[A.row_offset + row]));
       }
-      if (irregular) {
-        // ---------------- irregular tile, long rows: one warp per row, lane-strided partial sums + a fixed
-        // shuffle tree (deterministic; not the sequential order, so not bit-identical to the CPU sum) ----------------
-        const int lane = tid & 31, warp = tid >> 5;
-        for (uint32_t r2 = warp; r2 < nrows; r2 += kBlock / 32) {
-          const uint32_t grow = t.row_begin + r2;
-          uint32_t rs = B.rptr[grow - rb], re = B.rptr[grow + 1 - rb];
-          if (MODE != ABFT_MODE_CONSTRAINTS) {
-            rs = min(max(rs, t.nnz_begin), t.nnz_end);
-            re = min(max(re, rs), t.nnz_end);
-          }
-          // same admission test as the per-thread pass: inside the window, longer than kSeqRowMax
-          if (!(rs >= t.nnz_begin && re <= t.nnz_end && rs <= re) || re - rs <= kSeqRowMax) continue;
-          if (MODE == ABFT_MODE_CONSTRAINTS && !constraints_fast_ok_row(B.cols + (rs - cb), re - rs, A.n_cols, lane)) {
-            if (lane == 0) {
-              const double sum = constraints_careful(grow, rs, re);
-              y[grow] = sum;
-              dot_part = __dadd_rn(dot_part, __dmul_rn(sum, x[A.row_offset + grow]));
-            }
-            continue;
-          }
-          double part = 0.0;
-          for (uint32_t i = rs + lane; i < re; i += 32) part = __dadd_rn(part, B.vals[i - vb]);
-          part = warp_sum(part);
-          if (lane == 0) {
-            y[grow] = part;
-            dot_part = __dadd_rn(dot_part, __dmul_rn(part, x[A.row_offset + grow]));
-          }
-        }
-      }
+    }
+    if (dynamic) {
+      const double wp = warp_sum(dot_part);
+      if ((tid & 31) == 0) s_wdot[it & 1u][tid >> 5] = wp;
     }
     __syncthreads();  // everyone is done with stage `st`: it may be refilled
   }
-
-  // fused dot(vec, result): CTA partial, then the grid-wide deterministic sum
-  const double mine = block_sum(dot_part, s_warp);
-  grid_sum_finalize(mine, red, s_warp);
+  if (dynamic && tid == 0 && it > 0) {
+    // the last tile's dot() partial
+    const double *wd = s_wdot[(it - 1) & 1u];
+    double tp = wd[0];
+#pragma unroll
+    for (int k = 1; k < kBlock / 32; k++) tp = __dadd_rn(tp, wd[k]);
+    red.partials[s_tidx[(it - 1) % kStages]] = tp;
+  }
+  // fused dot(vec, result): CTA partials (static) or the per-tile partials (dynamic), then the grid-wide deterministic sum
+  const double mine = dynamic ? 0.0 : block_sum(dot_part, s_warp);
+  const bool last = grid_sum_finalize(mine, red, s_warp, dynamic ? A.n_tiles : 0u);
+  if (dynamic && last && tid == 0) *A.tile_counter = 0u;  // every CTA has drawn its last tile: ready for the next launch
 }
 
 }  // namespace abft

@@ -155,6 +155,101 @@ def test_spmv_long_rows(pkg, O):
         ctx.close()
 
 
+def _irregular_big(mg):
+    # ~2000 tiles of every kind (regular, irregular, rows longer than a tile): several tiles per CTA,
+    # drawn from the tile counter of the dynamic schedule
+    return mg.powerlaw(200_000, 4_000_000, max_deg=3000, seed=6)
+
+
+@pytest.mark.parametrize("mode", ["none", "constraints", "sec7", "secded"])
+def test_spmv_dynamic_schedule(pkg, O, mode):
+    """Matrices with irregular tiles are scheduled dynamically (CTAs draw tiles from a counter): result[] and the
+    fused dot(vec, result) must not depend on which CTA ran which tile -- bitwise equal from launch to launch --
+    and the counter must be ready again for the next launch."""
+    t = _irregular_big(pkg.matgen)
+    vec = np.random.default_rng(5).standard_normal(t.N)
+    ctx, A, om = make(pkg, O, mode, t)
+    assert ctx.L.abft_cuda_matrix_tiles(A.handle) > 3 * 592
+    v, w = ctx.create_vector(t.N), ctx.create_vector(t.N)
+    ctx.upload(v, vec)
+    runs = []
+    for _ in range(3):
+        ctx.upload(w, np.zeros(t.N))
+        ctx.spmv(A, v, w)
+        runs.append((ctx.download(w).view(np.uint64).copy(), np.float64(ctx.dot(v, w)).view(np.uint64)))
+    events, fatal = ctx.poll_events()
+    assert not fatal and events == []
+    for y_bits, dot_bits in runs[1:]:
+        assert np.array_equal(y_bits, runs[0][0]) and dot_bits == runs[0][1]
+    y = runs[0][0].view(np.float64)
+    y0, _, _ = om.spmv(vec)
+    lens = np.bincount(t.rows, minlength=t.N)
+    seq = lens <= 32
+    assert np.array_equal(y[seq].view(np.uint64), y0[seq].view(np.uint64))
+    scale = np.abs(t.vals).max() * np.abs(vec).max() * int(lens.max())
+    assert np.max(np.abs(y - y0)) <= 1e-13 * scale
+    exact = O.lib().orc_dot(vec, y0, t.N)
+    assert abs(runs[0][1].view(np.float64) - exact) <= RTOL * abs(exact)
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["sed", "sec7", "sec8", "secded"])
+def test_faults_in_irregular_tiles(pkg, O, mode):
+    """Single flips in short rows, in rows longer than 32 and in rows longer than a tile of a power-law matrix:
+    same events, same repaired matrix as the oracle."""
+    t = _irregular_big(pkg.matgen)
+    vec = np.random.default_rng(6).standard_normal(t.N)
+    lens = np.bincount(t.rows, minlength=t.N)
+    rowptr = np.concatenate([[0], np.cumsum(lens)])
+    short = int(np.flatnonzero((lens > 3) & (lens <= 32))[100])
+    mid = int(np.flatnonzero((lens > 100) & (lens <= 2048))[10])
+    longr = int(np.flatnonzero(lens > 2048)[0])
+    targets = [(int(rowptr[short]) + 2, 5), (int(rowptr[mid]) + 77, 40), (int(rowptr[longr]) + 2100, 70)]
+    for index, bit in targets if mode != "sed" else targets[:1]:
+        ctx, A, om = make(pkg, O, mode, t)
+        ctx.flip_bit(A, index, bit); om.flip(index, bit)
+        y, fatal, events, _ = gpu_spmv(ctx, A, vec)
+        y0, fatal0, ev0 = om.spmv(vec)
+        assert (fatal, events) == (fatal0, ev0) and len(events) == 1, (index, bit)
+        cols, _, vals = ctx.read_matrix(A)
+        assert np.array_equal(cols, om.cols) and np.array_equal(vals.view(np.uint64), om.values.view(np.uint64))
+        if not fatal:
+            scale = np.abs(t.vals).max() * np.abs(vec).max() * int(lens.max())
+            assert np.max(np.abs(y - y0)) <= 1e-13 * scale
+        ctx.close()
+
+
+def test_constraints_in_irregular_tiles(pkg, O):
+    """Column faults CONSTRAINTS must catch in the rows of a power-law matrix (short, > 32 elements, longer than
+    a tile), and row-pointer faults that send a row outside its tile."""
+    t = _irregular_big(pkg.matgen)
+    vec = np.random.default_rng(7).standard_normal(t.N)
+    lens = np.bincount(t.rows, minlength=t.N)
+    rowptr = np.concatenate([[0], np.cumsum(lens)])
+    short = int(np.flatnonzero((lens > 3) & (lens <= 32))[200])
+    mid = int(np.flatnonzero((lens > 100) & (lens <= 2048))[20])
+    longr = int(np.flatnonzero(lens > 2048)[1])
+    col_pokes = [(int(rowptr[short]) + 1, 1 << 30), (int(rowptr[short]) + 2, 0),        # too large / out of order
+                 (int(rowptr[mid]) + 50, 1 << 29), (int(rowptr[mid]) + 99, 0),
+                 (int(rowptr[longr]) + 2500, 1 << 28), (int(rowptr[longr]) + 10, 0)]
+    for index, value in col_pokes:
+        ctx, A, om = make(pkg, O, "constraints", t)
+        ctx._ck(ctx.L.abft_cuda_matrix_poke_col(ctx.ctx, A.handle, index, value), "poke")
+        om.cols[index] = value
+        y, fatal, events, _ = gpu_spmv(ctx, A, vec)
+        y0, fatal0, ev0 = om.spmv(vec)
+        assert (fatal, events) == (fatal0, ev0) and fatal, (index, value)
+        ctx.close()
+    for row, value in [(short, t.nnz + 5), (mid, 3), (mid + 1, int(rowptr[mid]) - 1)]:
+        ctx, A, om = make(pkg, O, "constraints", t)
+        ctx._ck(ctx.L.abft_cuda_matrix_poke_rowptr(ctx.ctx, A.handle, row, value), "poke")
+        om.rows[row] = value
+        y, fatal, events, _ = gpu_spmv(ctx, A, vec)
+        y0, fatal0, ev0 = om.spmv(vec)
+        assert (fatal, events) == (fatal0, ev0) and fatal, (row, value)
+        ctx.close()
+
+
 def test_fused_dot_equals_standalone_dot(pkg, O):
     t = pkg.matgen.poisson3d(20)
     rng = np.random.default_rng(1)
