@@ -569,9 +569,10 @@ int abft_cuda_vector_copy(abft_ctx *c, abft_vector *dst, const abft_vector *src)
 template <int MODE>
 static int spmv_resident_ctas(abft_ctx *c) {
   if (c->spmv_ctas_per_sm == 0) {
-    cudaFuncSetAttribute(spmv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvDynSmem);
+    cudaFuncSetAttribute(spmv_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvDynSmem);
+    cudaFuncSetAttribute(spmv_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvDynSmem);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_kernel<MODE>, kBlock, kSpmvDynSmem) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_kernel<MODE, false>, kBlock, kSpmvDynSmem) != cudaSuccess ||
         per_sm < 1)
       per_sm = 1;
     c->spmv_ctas_per_sm = per_sm;
@@ -584,7 +585,10 @@ static void launch_spmv_mode(abft_ctx *c, const abft_matrix *m, const double *x,
                              const int *active, const WaitSpec &wait) {
   LogRef L{c->d_log, c->h_flag};
   const int grid = std::min(m->n_tiles, spmv_resident_ctas<MODE>(c));
-  spmv_kernel<MODE><<<grid, kBlock, kSpmvDynSmem, c->stream>>>(m->view, x, y, L, red, active, wait);
+  if (m->view.tile_counter)
+    spmv_kernel<MODE, true><<<grid, kBlock, kSpmvDynSmem, c->stream>>>(m->view, x, y, L, red, active, wait);
+  else
+    spmv_kernel<MODE, false><<<grid, kBlock, kSpmvDynSmem, c->stream>>>(m->view, x, y, L, red, active, wait);
 }
 
 static int launch_spmv(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,

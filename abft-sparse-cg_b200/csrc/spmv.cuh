@@ -323,7 +323,8 @@ struct WaitSpec {
 #define ABFT_SPMV_MINB 4  // resident CTAs per SM the register allocation is tuned for
 #endif
 
-template <int MODE>
+// DYN: the dynamic tile schedule (A.tile_counter), compiled as its own kernel so that the static one carries none of it
+template <int MODE, bool DYN>
 __global__ void __launch_bounds__(kBlock, (MODE == ABFT_MODE_CRC32C) ? 3 : ABFT_SPMV_MINB)
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
             const int *__restrict__ active, WaitSpec wait) {
@@ -344,13 +345,14 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   // thread keeps its own dot() partial).  Dynamic (matrices with irregular tiles, whose cost per tile varies by
   // 5x): CTAs draw tiles from a counter; a tile's dot() contribution is then reduced per tile into
   // red.partials[tile], so the value published at the end is the same whichever CTA ran which tile.
-  const bool dynamic = A.tile_counter != nullptr;
-  __shared__ uint32_t s_next_static;  // (only thread 0 uses it: shared memory instead of a register in every thread)
-  Tile ahead{};                       // thread 0: descriptor and index of the next tile to issue
-  uint32_t ahead_idx = 0;
+  constexpr bool dynamic = DYN;
+  // static: this CTA's share of the tiles; dynamic: unknown, the loop ends at the "no more tiles" marker
+  const uint32_t n_my = (!DYN && A.n_tiles > blockIdx.x) ? (A.n_tiles - blockIdx.x + G - 1) / G : 0;
+  Tile ahead{};            // thread 0: descriptor and index of the next tile to issue
+  uint32_t ahead_idx = blockIdx.x - G;  // (static: tiles b, b+G, ...; wraps on purpose, the first fetch adds G)
   auto fetch_ahead = [&]() {
-    if (dynamic) ahead_idx = atomicAdd(A.tile_counter, 1u);
-    else { ahead_idx = s_next_static; s_next_static = ahead_idx + G; }
+    if (DYN) ahead_idx = atomicAdd(A.tile_counter, 1u);
+    else ahead_idx += G;
     if (ahead_idx < A.n_tiles) ahead = A.tiles[ahead_idx];  // consumed an iteration later: the latency overlaps a tile's work
     else ahead.info = kTileNone;
   };
@@ -396,7 +398,6 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   };
 
   if (tid == 0) {
-    s_next_static = blockIdx.x;
     for (int j = 0; j + 1 < kStages; j++) {
       fetch_ahead();
       s_tile[j] = ahead;
@@ -421,7 +422,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   double dot_part = 0.0;
 
   uint32_t it = 0;
-  for (;; it++) {
+  for (; DYN || it < n_my; it++) {
     const int st = (int)(it % kStages);
     // thread 0: bank the previous tile's dot() partial (dynamic schedule), refill the stage that tile released
     if (tid == 0) {
@@ -445,7 +446,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     }
     mbar_wait(&s_full[st], (it / kStages) & 1u);
     const Tile t = s_tile[st];  // (written by thread 0 before it armed the barrier)
-    if (t.info == kTileNone) break;
+    if (DYN && t.info == kTileNone) break;
     const bool irregular_tile = !(t.info & (kTileLongRow | kTileRegular)) && MODE != ABFT_MODE_CRC32C;
     const StageBuf &B = stage[st];
     if (dynamic) dot_part = 0.0;  // reduced per tile below
