@@ -284,10 +284,12 @@ static void build_tiles(const uint32_t *rowptr, uint32_t n_rows, std::vector<Til
     } else {
       const uint32_t nrows = e - r, nnz = rowptr[e] - start;
       info = nrows;
-      // thread-per-row pays max_len steps, element-parallel pays nnz/kBlock (+ a light row phase):
-      // rows of similar length (every stencil matrix) go thread-per-row
+      // thread-per-row pays max_len steps (a gather round trip every 4), element-parallel pays nnz/kBlock steps
+      // (+ the row phase): rows of similar length go thread-per-row (every stencil matrix) -- unless the tile is
+      // a handful of very long rows (3 rows of 680: one thread would walk 680 elements while 253 idle; measured
+      // 200k+ cycles for such a tile against 16k for the element-parallel path)
       const uint32_t mean_up = (nnz + nrows - 1) / nrows;
-      if (max_len <= 2 * mean_up + 4) info |= kTileRegular;
+      if (max_len <= 2 * mean_up + 4 && (uint64_t)max_len * 32u <= (uint64_t)nnz + 512u) info |= kTileRegular;
       info |= std::min(max_len, 0xFFFu) << kTileMaxLenShift;
     }
     tiles.push_back(Tile{r, start, rowptr[e], info});
