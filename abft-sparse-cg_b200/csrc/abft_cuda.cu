@@ -82,6 +82,7 @@ struct abft_ctx {
   int *h_loop = nullptr;            // mapped pinned mirror: [0] = iterations, [1] = next-active
   uint64_t launches = 0;
   int spmv_ctas_per_sm = 0;  // resident CTAs of this mode's spmv kernel (set at first launch)
+  int spmv_ctas_per_sm_dyn = 0;  // ... of its dynamic-schedule variant
   // fused dot(vec, result) left behind by the last spmv
   const double *dot_a = nullptr, *dot_b = nullptr;
   int dot_n = 0;
@@ -266,14 +267,15 @@ uint64_t abft_cuda_launch_count(const abft_ctx *c) { return c ? c->launches : 0;
 // ---------------------------------------------------------------------------
 // matrix
 // ---------------------------------------------------------------------------
-static void build_tiles(const uint32_t *rowptr, uint32_t n_rows, std::vector<Tile> &tiles) {
+static void build_tiles(const uint32_t *rowptr, uint32_t n_rows, uint32_t tile_nnz, std::vector<Tile> &tiles) {
+  tiles.clear();
   uint32_t r = 0;
   while (r < n_rows) {
     const uint32_t start = rowptr[r];
     uint32_t e = r;
     uint32_t max_len = 0;
     while (e < n_rows && (e - r) < (uint32_t)kTileRows && rowptr[e + 1] >= start &&
-           rowptr[e + 1] - start <= (uint32_t)kTileNnz) {
+           rowptr[e + 1] - start <= tile_nnz) {
       max_len = std::max(max_len, rowptr[e + 1] - rowptr[e]);
       e++;
     }
@@ -361,17 +363,23 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
   CKP(cudaFree(d_coo_rows));
   d_coo_rows = nullptr;
   std::vector<Tile> tiles;
-  build_tiles(h_rowptr.data(), (uint32_t)n_rows, tiles);
+  build_tiles(h_rowptr.data(), (uint32_t)n_rows, (uint32_t)kTileNnz, tiles);
   m->n_tiles = (int)tiles.size();
   if (m->n_tiles > kMaxPartials) {
     fail(-1, "matrix needs more spmv tiles than the reduction buffer holds", __FILE__, __LINE__);
     return nullptr;
   }
   // irregular tiles cost very different amounts (and the gathers make even equal tiles take 0.3x .. 2x the mean):
-  // such a matrix is scheduled dynamically, CTAs drawing tiles from a counter (spmv.cuh)
+  // such a matrix is scheduled dynamically, CTAs drawing (smaller: spmv.cuh, kTileNnzDyn) tiles from a counter
   bool irregular = false;
   for (const Tile &t : tiles) irregular |= !(t.info & kTileRegular);
   if (irregular && c->mode != ABFT_MODE_CRC32C) {
+    build_tiles(h_rowptr.data(), (uint32_t)n_rows, (uint32_t)kTileNnzDyn, tiles);
+    m->n_tiles = (int)tiles.size();
+    if (m->n_tiles > kMaxPartials) {
+      fail(-1, "matrix needs more spmv tiles than the reduction buffer holds", __FILE__, __LINE__);
+      return nullptr;
+    }
     CKP(cudaMalloc(&m->d_tile_counter, sizeof(unsigned int)));
     CKP(cudaMemset(m->d_tile_counter, 0, sizeof(unsigned int)));
   }
@@ -568,29 +576,37 @@ int abft_cuda_vector_copy(abft_ctx *c, abft_vector *dst, const abft_vector *src)
 }  // extern "C"
 
 // persistent grid: SMs x resident CTAs of this mode's kernel (never more CTAs than tiles)
-template <int MODE>
+template <int MODE, bool DYN>
 static int spmv_resident_ctas(abft_ctx *c) {
-  if (c->spmv_ctas_per_sm == 0) {
-    cudaFuncSetAttribute(spmv_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvDynSmem);
-    cudaFuncSetAttribute(spmv_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvDynSmem);
+  int &cached = DYN ? c->spmv_ctas_per_sm_dyn : c->spmv_ctas_per_sm;
+  if (cached == 0) {
+    const int smem = (int)SpmvCfg<DYN>::dyn_smem;
+    cudaFuncSetAttribute(spmv_kernel<MODE, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_kernel<MODE, false>, kBlock, kSpmvDynSmem) != cudaSuccess ||
-        per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_kernel<MODE, DYN>, kBlock, smem) != cudaSuccess || per_sm < 1)
       per_sm = 1;
-    c->spmv_ctas_per_sm = per_sm;
+    if (DYN) {
+      // leave the L1 what the stage buffers of the resident CTAs do not need (gathers in flight hold L1 lines)
+      const int need_kb = (per_sm * (smem + 1024) + 1023) / 1024;
+      cudaFuncSetAttribute(spmv_kernel<MODE, DYN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           std::min(100, (need_kb * 100 + 227) / 228));
+    }
+    cached = per_sm;
   }
-  return c->spmv_ctas_per_sm * c->num_sms;
+  return cached * c->num_sms;
 }
 
 template <int MODE>
 static void launch_spmv_mode(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,
                              const int *active, const WaitSpec &wait) {
   LogRef L{c->d_log, c->h_flag};
-  const int grid = std::min(m->n_tiles, spmv_resident_ctas<MODE>(c));
-  if (m->view.tile_counter)
-    spmv_kernel<MODE, true><<<grid, kBlock, kSpmvDynSmem, c->stream>>>(m->view, x, y, L, red, active, wait);
-  else
-    spmv_kernel<MODE, false><<<grid, kBlock, kSpmvDynSmem, c->stream>>>(m->view, x, y, L, red, active, wait);
+  if (m->view.tile_counter) {
+    const int grid = std::min(m->n_tiles, spmv_resident_ctas<MODE, true>(c));
+    spmv_kernel<MODE, true><<<grid, kBlock, SpmvCfg<true>::dyn_smem, c->stream>>>(m->view, x, y, L, red, active, wait);
+  } else {
+    const int grid = std::min(m->n_tiles, spmv_resident_ctas<MODE, false>(c));
+    spmv_kernel<MODE, false><<<grid, kBlock, SpmvCfg<false>::dyn_smem, c->stream>>>(m->view, x, y, L, red, active, wait);
+  }
 }
 
 static int launch_spmv(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,

@@ -32,6 +32,14 @@
 namespace abft {
 
 constexpr int kTileNnz = 2048;
+// Matrices with irregular tiles (dynamic schedule) are gather-bound, and a gather in flight holds an L1 line: with
+// 4 CTAs x 52 KB of stage buffers the SM's 256 KB are all shared memory and the ~28 KB of L1 left cap the gathers in
+// flight (measured: same kernel, carveout forced down to 164 KB / 3 CTAs: 0.41 -> 0.32 ms).  Their tiles are half
+// the size, so that 4 CTAs need 104 KB and the L1 keeps ~120 KB.
+#ifndef ABFT_TILE_DYN
+#define ABFT_TILE_DYN 1024
+#endif
+constexpr int kTileNnzDyn = ABFT_TILE_DYN;
 constexpr int kTileRows = kBlock;  // 256: one row per thread
 constexpr int kStages = 2;
 constexpr uint32_t kSeqRowMax = 32;  // irregular tiles: rows up to this long are summed sequentially by one thread
@@ -70,12 +78,18 @@ struct MatView {
 // one pipeline stage of staged tile data (windows start at 16-byte aligned indices)
 // (+16: the windows are rounded out to 16 bytes, and the unrolled row walk may read up to 6 slots
 // past a row's end)
-struct __align__(16) StageBuf {
-  double vals[kTileNnz + 16];
-  uint32_t cols[kTileNnz + 16];
+template <int TN>
+struct __align__(16) StageBufT {
+  double vals[TN + 16];
+  uint32_t cols[TN + 16];
   uint32_t rptr[kTileRows + 8];
 };
-constexpr size_t kSpmvDynSmem = sizeof(StageBuf) * kStages;
+template <bool DYN>
+struct SpmvCfg {
+  static constexpr int tile_nnz = DYN ? kTileNnzDyn : kTileNnz;
+  using Stage = StageBufT<tile_nnz>;
+  static constexpr size_t dyn_smem = sizeof(Stage) * kStages;
+};
 
 // ---- PTX: mbarrier + TMA bulk copy (global -> shared) -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -329,6 +343,8 @@ __global__ void __launch_bounds__(kBlock, (MODE == ABFT_MODE_CRC32C) ? 3 : ABFT_
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
             const int *__restrict__ active, WaitSpec wait) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
+  using StageBuf = typename SpmvCfg<DYN>::Stage;
+  constexpr size_t kSpmvDynSmem = SpmvCfg<DYN>::dyn_smem;
   StageBuf *stage = reinterpret_cast<StageBuf *>(dyn_smem);
   __shared__ __align__(8) uint64_t s_full[kStages];
   __shared__ Tile s_tile[kStages];
