@@ -586,7 +586,9 @@ static int spmv_resident_ctas(abft_ctx *c) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_kernel<MODE, DYN>, kBlock, smem) != cudaSuccess || per_sm < 1)
       per_sm = 1;
     if (DYN) {
-      // leave the L1 what the stage buffers of the resident CTAs do not need (gathers in flight hold L1 lines)
+      // leave the L1 what the stage buffers of the resident CTAs do not need (gathers in flight hold L1 lines);
+      // a fifth CTA (mode none has the registers for it) would take the L1 back
+      per_sm = std::min(per_sm, 4);
       const int need_kb = (per_sm * (smem + 1024) + 1023) / 1024;
       cudaFuncSetAttribute(spmv_kernel<MODE, DYN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            std::min(100, (need_kb * 100 + 227) / 228));

@@ -34,10 +34,11 @@ namespace abft {
 constexpr int kTileNnz = 2048;
 // Matrices with irregular tiles (dynamic schedule) are gather-bound, and a gather in flight holds an L1 line: with
 // 4 CTAs x 52 KB of stage buffers the SM's 256 KB are all shared memory and the ~28 KB of L1 left cap the gathers in
-// flight (measured: same kernel, carveout forced down to 164 KB / 3 CTAs: 0.41 -> 0.32 ms).  Their tiles are half
-// the size, so that 4 CTAs need 104 KB and the L1 keeps ~120 KB.
+// flight (measured: same kernel, carveout forced down to 164 KB / 3 CTAs: 0.41 -> 0.32 ms).  Their tiles are smaller,
+// so that 4 CTAs need 160 KB and the L1 keeps 92 KB.  Measured on the power-law workload (sec7, 4 CTAs per SM):
+// 2048 -> 0.40 ms (L1 28 KB), 1536 -> 0.295 (92 KB), 1024 -> 0.335 (124 KB), 768 -> 0.378 (156 KB).
 #ifndef ABFT_TILE_DYN
-#define ABFT_TILE_DYN 1024
+#define ABFT_TILE_DYN 1536
 #endif
 constexpr int kTileNnzDyn = ABFT_TILE_DYN;
 constexpr int kTileRows = kBlock;  // 256: one row per thread
