@@ -18,9 +18,15 @@
 //    separate multiply and add, i.e. exactly the reference's
 //    `tmp += values[i] * vec[col]`: result[] is bit-identical to the CPU target.
 //  * Irregular tiles (power-law rows): element-parallel check + product into shared
-//    memory, then thread r adds row r's products in element order (same bits).
-//  * A row longer than kTileNnz is a tile of its own, streamed from global memory in
+//    memory, one CTA barrier, then a warp-local row phase: a lane adds its row's products
+//    in element order (same bits as the CPU sum) for rows of up to 32 elements, the warp
+//    takes its lanes' longer rows one at a time (lane-strided sums + shuffle tree).
+//  * A row longer than a tile is a tile of its own, streamed from global memory in
 //    chunks with a tree reduction (not bit-identical to the sequential sum; < 1e-10).
+//  * Matrices with irregular tiles run the DYN variant: tiles are drawn from a device
+//    counter (their cost varies 5x), dot() partials are kept per tile so the result does
+//    not depend on the schedule, and tiles are smaller so that the L1 keeps 92 KB for the
+//    gathers in flight (profiles/r1_powerlaw_investigation.md).
 //  * The owning lane corrects a faulty element in registers, writes it back to
 //    global memory and logs the event; dot(vec, result) is reduced in the epilogue.
 // CONSTRAINTS element events carry their global row in `bit` (the host orders them
