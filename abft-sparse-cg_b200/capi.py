@@ -36,6 +36,8 @@ SYMBOLS = [
     "abft_cuda_comm_attach_peer_ptrs", "abft_cuda_comm_set_plan", "abft_cuda_dist_push", "abft_cuda_dist_calc_p",
     "abft_cuda_dist_spmv", "abft_cuda_dist_dot", "abft_cuda_dist_calc_xr", "abft_cuda_dist_cg_solve",
     "abft_cuda_dist_dot_async", "abft_cuda_dist_calc_xr_async",
+    "abft_cuda_coo_matrix_create", "abft_cuda_coo_matrix_destroy", "abft_cuda_coo_matrix_nnz",
+    "abft_cuda_coo_matrix_read", "abft_cuda_coo_spmv", "abft_cuda_coo_flip_bit", "abft_cuda_coo_format_event",
 ]
 
 
@@ -130,6 +132,13 @@ def load():
     sig("abft_cuda_dist_dot_async", i32, vp, vp, vp, vp, i32p)
     sig("abft_cuda_dist_calc_xr_async", i32, vp, vp, vp, vp, vp, vp, f64, i32p)
     sig("abft_cuda_dist_cg_solve", i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, i32, f64p)
+    sig("abft_cuda_coo_matrix_create", vp, vp, vp, vp, vp, i32, i32)
+    sig("abft_cuda_coo_matrix_destroy", None, vp, vp)
+    sig("abft_cuda_coo_matrix_nnz", i32, vp)
+    sig("abft_cuda_coo_matrix_read", i32, vp, vp, vp)
+    sig("abft_cuda_coo_spmv", i32, vp, vp, vp, vp)
+    sig("abft_cuda_coo_flip_bit", i32, vp, vp, i32, i32)
+    sig("abft_cuda_coo_format_event", i32, C.POINTER(Event), C.c_char_p, i32)
     _lib = L
     return L
 

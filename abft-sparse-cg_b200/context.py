@@ -229,6 +229,64 @@ class CUDAContext:
             itr += 1
         return itr, np.asarray(hist)
 
+    # ---- COO format (the reference's cg-coo; COO/CPUContext.cpp) ----
+    COO_ELEM = np.dtype([("col", np.uint32), ("row", np.uint32), ("value", np.float64)])
+
+    def create_coo_matrix(self, columns, rows, values, N):
+        c = np.ascontiguousarray(columns, dtype=np.uint32)
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        h = self.L.abft_cuda_coo_matrix_create(self.ctx, _ptr(c), _ptr(r), _ptr(v), int(N), int(c.shape[0]))
+        if not h:
+            raise RuntimeError("cuda target: coo_matrix_create failed: " + capi.last_error())
+        m = Matrix(h, int(N), int(c.shape[0]))
+        m.coo = True
+        return m
+
+    def destroy_coo_matrix(self, mat):
+        self.L.abft_cuda_coo_matrix_destroy(self.ctx, mat.handle)
+        mat.handle = None
+
+    def read_coo_matrix(self, mat) -> np.ndarray:
+        out = np.zeros(max(mat.nnz, 1), dtype=self.COO_ELEM)
+        self._ck(self.L.abft_cuda_coo_matrix_read(self.ctx, mat.handle, _ptr(out)), "coo_matrix_read")
+        return out[:mat.nnz]
+
+    def coo_spmv(self, mat, vec, result):
+        self._ck(self.L.abft_cuda_coo_spmv(self.ctx, mat.handle, vec.handle, result.handle), "coo_spmv")
+
+    def coo_flip_bit(self, mat, index, bit):
+        self._ck(self.L.abft_cuda_coo_flip_bit(self.ctx, mat.handle, int(index), int(bit)), "coo_flip_bit")
+
+    def coo_format_event(self, ev) -> str:
+        e = capi.Event(*ev)
+        buf = C.create_string_buffer(128)
+        self.L.abft_cuda_coo_format_event(C.byref(e), buf, 128)
+        return buf.value.decode()
+
+    def coo_cg(self, A, b, x, r, p, w, max_itrs, conv_threshold):
+        """cg.cpp:83-118 over a COO matrix -> (iterations, rr history, events, fatal)."""
+        self.copy_vector(r, b)
+        self.copy_vector(p, r)
+        rr = self.dot(r, r)
+        hist, events = [], []
+        itr = 0
+        while itr < max_itrs and rr > conv_threshold:
+            self.coo_spmv(A, p, w)
+            pw = self.dot(p, w)
+            ev, fatal = self.poll_events()
+            events += ev
+            if fatal:
+                return itr, np.asarray(hist), events, True
+            alpha = rr / pw
+            rr_new = self.calc_xr(x, r, p, w, alpha)
+            beta = rr_new / rr
+            self.calc_p(p, r, beta)
+            rr = rr_new
+            hist.append(rr)
+            itr += 1
+        return itr, np.asarray(hist), events, False
+
     def cg_solve_device(self, A, b, x, r, p, w, max_itrs, conv_threshold, check_every=16):
         """Device-resident loop (abft_cuda_cg_solve) -> (iterations, final rr)."""
         rr = C.c_double(0.0)

@@ -12,6 +12,7 @@
 #include "ecc.cuh"
 #include "encode.cuh"
 #include "spmv.cuh"
+#include "coo.cuh"
 #include "vecops.cuh"
 
 using namespace abft;
@@ -1203,6 +1204,161 @@ int abft_cuda_dist_cg_solve(abft_ctx *c, abft_comm *m, abft_matrix *A, const abf
   }
   return cg_solve_impl(c, m->world > 1 ? m : nullptr, A, b, x, r, p_local, p_full, w, max_itrs, conv_threshold,
                        check_every, rr_out);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// COO format (the reference's cg-coo): see coo.cuh for the design and its status
+// ---------------------------------------------------------------------------
+struct abft_coo_matrix {
+  CooView view{};
+  uint32_t *d_perm = nullptr, *d_colptr = nullptr;
+};
+
+template <int MODE>
+static void launch_coo_spmv_mode(abft_ctx *c, const abft_coo_matrix *m, const double *vec, double *result) {
+  LogRef L{c->d_log, c->h_flag};
+  const int grid = std::max(1, std::min((int)((m->view.N + kBlock - 1) / kBlock), c->num_sms * 8));
+  coo_spmv_kernel<MODE><<<grid, kBlock, 0, c->stream>>>(m->view, vec, result, L);
+  coo_stray_kernel<MODE><<<1, 32, 0, c->stream>>>(m->view, vec, result);
+}
+
+extern "C" {
+
+int abft_cuda_coo_format_event(const abft_event *e, char *buf, int buflen) {
+  switch (e->kind) {  // COO/CPUContext.cpp:159,164,177,187; the ECC messages are the CSR target's
+    case ABFT_EV_ROW_SIZE: return snprintf(buf, buflen, "row size constraint violated for index %d", (int)e->index);
+    case ABFT_EV_ROW_ORDER: return snprintf(buf, buflen, "row index order violated at index %d", (int)e->index);
+    case ABFT_EV_COL_SIZE: return snprintf(buf, buflen, "column size constraint violated for index %d", (int)e->index);
+    case ABFT_EV_COL_ORDER: return snprintf(buf, buflen, "column index order violated at index %d", (int)e->index);
+    default: return abft_cuda_format_event(e, buf, buflen);
+  }
+}
+
+abft_coo_matrix *abft_cuda_coo_matrix_create(abft_ctx *c, const uint32_t *columns, const uint32_t *rows,
+                                             const double *values, int N, int nnz) {
+  if (!c || N < 0 || nnz < 0 || (nnz > 0 && (!columns || !rows || !values))) {
+    fail(-1, "bad arguments to coo_matrix_create", __FILE__, __LINE__);
+    return nullptr;
+  }
+  if (c->mode == ABFT_MODE_CRC32C) {
+    fail(-1, "crc32c is a CSR-only mode (the reference's COO target has none, and this repository defines none)",
+         __FILE__, __LINE__);
+    return nullptr;
+  }
+  if (c->mode >= ABFT_MODE_SED && (unsigned)N > (1u << 24)) {
+    fail(-1, "ECC modes keep the check bits in column bits 24..31: N must be <= 2^24", __FILE__, __LINE__);
+    return nullptr;
+  }
+  std::vector<uint32_t> colptr((size_t)N + 1, 0u), perm((size_t)std::max(nnz, 1));
+  if (!coo_build_groups(columns, N, nnz, colptr.data(), perm.data())) {
+    fail(-1, "coo_matrix_create: column index out of range", __FILE__, __LINE__);
+    return nullptr;
+  }
+  CKP(cudaSetDevice(c->device));
+  abft_coo_matrix *m = new abft_coo_matrix();
+  const size_t nz = (size_t)std::max(nnz, 1);
+  uint32_t *d_cols = nullptr, *d_rows = nullptr;
+  double *d_vals = nullptr;
+  struct Cleanup {
+    abft_coo_matrix *&m;
+    uint32_t *&a, *&b;
+    double *&v;
+    bool armed = true;
+    ~Cleanup() {
+      cudaFree(a);
+      cudaFree(b);
+      cudaFree(v);
+      if (!armed) return;
+      cudaFree(m->view.elements);
+      cudaFree(m->view.stray);
+      cudaFree(m->d_perm);
+      cudaFree(m->d_colptr);
+      delete m;
+    }
+  } cleanup{m, d_cols, d_rows, d_vals};
+  CKP(cudaMalloc(&m->view.elements, sizeof(uint4) * nz));
+  CKP(cudaMalloc(&m->view.stray, sizeof(uint32_t) * (1 + kMaxStray)));
+  CKP(cudaMalloc(&m->d_perm, sizeof(uint32_t) * nz));
+  CKP(cudaMalloc(&m->d_colptr, sizeof(uint32_t) * ((size_t)N + 1)));
+  CKP(cudaMalloc(&d_cols, sizeof(uint32_t) * nz));
+  CKP(cudaMalloc(&d_rows, sizeof(uint32_t) * nz));
+  CKP(cudaMalloc(&d_vals, sizeof(double) * nz));
+  CKP(cudaMemsetAsync(m->view.stray, 0, sizeof(uint32_t), c->stream));
+  CKP(cudaMemcpyAsync(m->d_colptr, colptr.data(), sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, c->stream));
+  if (nnz > 0) {
+    CKP(cudaMemcpyAsync(m->d_perm, perm.data(), sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    CKP(cudaMemcpyAsync(d_cols, columns, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    CKP(cudaMemcpyAsync(d_rows, rows, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    CKP(cudaMemcpyAsync(d_vals, values, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    coo_encode_kernel<<<c->num_sms * 8, kBlock, 0, c->stream>>>(c->mode, d_cols, d_rows, d_vals, m->view.elements,
+                                                                 (uint32_t)nnz);
+    c->launches++;
+    CKP(cudaGetLastError());
+  }
+  CKP(cudaStreamSynchronize(c->stream));  // the host staging vectors go out of scope
+  m->view.perm = m->d_perm;
+  m->view.colptr = m->d_colptr;
+  m->view.N = (uint32_t)N;
+  m->view.nnz = (uint32_t)nnz;
+  cleanup.armed = false;
+  return m;
+}
+
+void abft_cuda_coo_matrix_destroy(abft_ctx *c, abft_coo_matrix *m) {
+  if (!m) return;
+  if (c) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(m->view.elements);
+  cudaFree(m->view.stray);
+  cudaFree(m->d_perm);
+  cudaFree(m->d_colptr);
+  delete m;
+}
+
+int abft_cuda_coo_matrix_nnz(const abft_coo_matrix *m) { return m ? (int)m->view.nnz : -1; }
+
+int abft_cuda_coo_matrix_read(abft_ctx *c, const abft_coo_matrix *m, void *elements_out) {
+  REQUIRE(c && m && elements_out, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (m->view.nnz) CK(cudaMemcpy(elements_out, m->view.elements, sizeof(uint4) * m->view.nnz, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int abft_cuda_coo_flip_bit(abft_ctx *c, abft_coo_matrix *m, int index, int bit) {
+  REQUIRE(c && m, "null argument");
+  REQUIRE(bit >= 0 && bit < 128, "bit out of range");
+  REQUIRE(index >= 0 && (uint32_t)index < m->view.nnz, "element index out of range");
+  CK(cudaSetDevice(c->device));
+  coo_flip_bit_kernel<<<1, 32, 0, c->stream>>>(m->view.elements, (uint32_t)index, bit);
+  c->launches++;
+  c->epoch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int abft_cuda_coo_spmv(abft_ctx *c, abft_coo_matrix *m, const abft_vector *vec, abft_vector *result) {
+  REQUIRE(c && m && vec && result, "null argument");
+  REQUIRE((uint32_t)result->N >= m->view.N && (uint32_t)vec->N >= m->view.N, "coo_spmv: vectors shorter than N");
+  REQUIRE(vec->d != result->d, "coo_spmv: vec and result must not alias");
+  CK(cudaSetDevice(c->device));
+  switch (c->mode) {
+    case ABFT_MODE_NONE: launch_coo_spmv_mode<ABFT_MODE_NONE>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_CONSTRAINTS: launch_coo_spmv_mode<ABFT_MODE_CONSTRAINTS>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_SED: launch_coo_spmv_mode<ABFT_MODE_SED>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_SEC7: launch_coo_spmv_mode<ABFT_MODE_SEC7>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_SEC8: launch_coo_spmv_mode<ABFT_MODE_SEC8>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_SECDED: launch_coo_spmv_mode<ABFT_MODE_SECDED>(c, m, vec->d, result->d); break;
+    default: return fail(-1, "coo_spmv: mode has no COO form", __FILE__, __LINE__);
+  }
+  c->launches += 2;
+  c->epoch++;  // (no fused dot here: a later abft_cuda_dot launches its own kernel)
+  CK(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -1,0 +1,260 @@
+// coo.cuh -- the COO format of the reference's second executable (cg-coo): 128-bit elements
+// {col, row, value} with the check byte in col bits 24..31 (reference: COO/ecc.h:7-16, COO/CPUContext.cpp).
+//
+// STATUS: written against oracle/coo_oracle.c (which is pinned against the reference), compiled for sm_100a,
+// NOT YET RUN ON A GPU -- the round's GPU budget was spent before this file existed.  Its GPU tests
+// (tests/test_gpu_coo.py) are opt-in (ABFT_COO_GPU_TESTS=1) until they have been seen green on hardware.
+//
+// The reference's loop is a scatter: for every element in index order, result[col] += value * vec[row]
+// (COO/CPUContext.cpp:104-121).  Each output entry therefore accumulates its elements in ascending element
+// index.  Here: create_matrix groups the element indices by output entry once (`perm`, `colptr`: a
+// stable counting sort by column), and thread c walks group c in order -- check, repair, multiply, add --
+// so result[] has the reference's bits, without atomics.  The elements stay where the caller put them
+// (fault indices and inject_bitflip refer to that order) and are read through `perm` with 128-bit loads.
+//
+// An index fault that no check repairs (mode none, an undetected double flip, a mis-corrected multi-bit
+// fault) changes where an element's product belongs.  The walking thread notices (the element's column is
+// not the group's), leaves it out and puts it on a short "stray" list; a one-thread fix-up kernel then
+// recomputes the output entries the strays now point at, merging them into those groups by element index.
+// Result: the reference's result[] in every case the reference defines (it reads/writes out of bounds when
+// an index leaves [0, N): such an element is dropped here and in the oracle).
+#pragma once
+#include "common.cuh"
+
+namespace abft {
+
+constexpr bool coo_is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
+
+// mask of parity p (1..7) over word (0..3) of the element {col, row, value lo, value hi}, including the parity
+// bit itself (stored in col bit 32-p).  Rule behind the reference's 28 constants (COO/ecc.h:18-51): the 120 data
+// bits -- every element bit except the check byte 24..31 -- take the non-power-of-two code positions 3,5,6,7,9,...
+constexpr uint32_t coo_mask(int p, int word) {
+  uint32_t m = 0;
+  uint32_t pos = 3;
+  for (int ebit = 0; ebit < 128; ebit++) {
+    if (ebit >= 24 && ebit < 32) continue;
+    while (coo_is_pow2(pos)) pos++;
+    if (((pos >> (p - 1)) & 1u) && ebit / 32 == word) m |= 1u << (ebit % 32);
+    pos++;
+  }
+  if (word == 0) m |= 1u << (32 - p);
+  return m;
+}
+static_assert(coo_mask(1, 0) == 0x80AAAD5Bu, "P1 word0 (COO/ecc.h:18)");
+static_assert(coo_mask(7, 2) == 0xFFFFFFFEu, "P7 word2 (COO/ecc.h:50)");
+static_assert(coo_mask(6, 1) == 0xFFFFFFFCu, "P6 word1 (COO/ecc.h:44)");
+
+template <int P>
+struct CM {
+  static constexpr uint32_t w0 = coo_mask(P, 0), w1 = coo_mask(P, 1), w2 = coo_mask(P, 2), w3 = coo_mask(P, 3);
+};
+
+template <int P>
+__device__ __forceinline__ uint32_t coo_parity_bit(const uint4 &e) {
+  uint32_t t = 0;
+  if (CM<P>::w0) t ^= e.x & CM<P>::w0;
+  if (CM<P>::w1) t ^= e.y & CM<P>::w1;
+  if (CM<P>::w2) t ^= e.z & CM<P>::w2;
+  if (CM<P>::w3) t ^= e.w & CM<P>::w3;
+  return __popc(t) & 1u;
+}
+
+// ecc_compute_overall_parity (COO/ecc.h:108-112)
+__device__ __forceinline__ uint32_t coo_overall(const uint4 &e) { return __popc(e.x ^ e.y ^ e.z ^ e.w) & 1u; }
+
+// ecc_compute_col8 (COO/ecc.h:63-100): parity p -> bit 32-p
+__device__ __forceinline__ uint32_t coo_syndrome(const uint4 &e) {
+  return (coo_parity_bit<1>(e) << 31) | (coo_parity_bit<2>(e) << 30) | (coo_parity_bit<3>(e) << 29) |
+         (coo_parity_bit<4>(e) << 28) | (coo_parity_bit<5>(e) << 27) | (coo_parity_bit<6>(e) << 26) |
+         (coo_parity_bit<7>(e) << 25);
+}
+
+// ecc_get_flipped_bit_col8 (COO/ecc.h:116-134).  syndrome != 0.
+__device__ __forceinline__ uint32_t coo_flipped_bit(uint32_t syndrome) {
+  const uint32_t position = __brev(syndrome) & 0x7Fu;
+  const uint32_t lz = __clz(position);
+  if ((position & (position - 1)) == 0) return lz;  // parity bit p itself: col bit 32-p
+  const uint32_t rank = position - (32 - lz) - 1;
+  return rank >= 24 ? rank + 8 : rank;               // data bits from rank 24 on sit behind the check byte
+}
+
+__device__ __forceinline__ uint32_t &coo_word(uint4 &e, uint32_t w) {
+  return w == 0 ? e.x : (w == 1 ? e.y : (w == 2 ? e.z : e.w));
+}
+
+// generate_ecc_bits (COO/CPUContext.cpp:196-199 SED, 230-233 SEC7, 269-273 SEC8, 320-324 SECDED)
+__global__ void __launch_bounds__(kBlock)
+coo_encode_kernel(int mode, const uint32_t *__restrict__ cols, const uint32_t *__restrict__ rows,
+                  const double *__restrict__ values, uint4 *__restrict__ elements, uint32_t nnz) {
+  const uint32_t stride = gridDim.x * kBlock;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nnz; i += stride) {
+    const double v = values[i];
+    uint4 e = make_uint4(cols[i], rows[i], (uint32_t)__double2loint(v), (uint32_t)__double2hiint(v));
+    if (mode == ABFT_MODE_SED) {
+      e.x |= coo_overall(e) << 31;
+    } else if (mode == ABFT_MODE_SEC7) {
+      e.x |= coo_syndrome(e);
+    } else if (mode == ABFT_MODE_SEC8 || mode == ABFT_MODE_SECDED) {
+      e.x |= coo_syndrome(e);
+      e.x |= coo_overall(e) << 24;
+    }
+    elements[i] = e;
+  }
+}
+
+// the 4-byte read-modify-write of inject_bitflip (COO/CPUContext.cpp:138)
+__global__ void coo_flip_bit_kernel(uint4 *elements, uint32_t index, int bit) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  reinterpret_cast<uint32_t *>(elements + index)[bit / 32] ^= 1u << (bit % 32);
+}
+
+constexpr uint32_t kMaxStray = 1024;
+
+// Host side of create_matrix: group the element indices by output entry (= column), ascending inside a group
+// (a stable counting sort).  colptr gets N+1 entries, perm nnz.  Returns false if a column is out of range.
+inline bool coo_build_groups(const uint32_t *columns, int N, int nnz, uint32_t *colptr, uint32_t *perm) {
+  for (int j = 0; j <= N; j++) colptr[j] = 0;
+  for (int i = 0; i < nnz; i++) {
+    if (columns[i] >= (uint32_t)N) return false;
+    colptr[columns[i] + 1]++;
+  }
+  for (int j = 0; j < N; j++) colptr[j + 1] += colptr[j];
+  // fill each group front to back; colptr[j] is advanced while filling and restored afterwards
+  for (int i = 0; i < nnz; i++) perm[colptr[columns[i]]++] = (uint32_t)i;
+  for (int j = N; j > 0; j--) colptr[j] = colptr[j - 1];
+  colptr[0] = 0;
+  return true;
+}
+
+struct CooView {
+  uint4 *elements;         // [nnz] {col | check byte, row, value lo, value hi}, caller's order
+  const uint32_t *perm;    // [nnz] element indices grouped by output entry, ascending inside a group
+  const uint32_t *colptr;  // [N+1] group boundaries in perm
+  uint32_t *stray;         // [1 + kMaxStray]: count, then element indices (see the file comment)
+  uint32_t N, nnz;
+};
+
+// Check (and repair) one element the way the mode's spmv does; logs what the reference prints.
+// Returns false if the reference would have exit(1)ed at this element.
+template <int MODE>
+__device__ __forceinline__ bool coo_check(uint4 &e, uint32_t i, const CooView &A, const LogRef &L) {
+  if (MODE == ABFT_MODE_CONSTRAINTS) {
+    // COO/CPUContext.cpp:155-187, in the reference's order; the first violation is fatal.  (`bit` carries the
+    // index so that the host orders these among themselves by element; it is cleared before reporting.)
+    if (e.y >= A.N) { log_event(L, ABFT_EV_ROW_SIZE, i, 0); return false; }
+    if (e.x >= A.N) { log_event(L, ABFT_EV_COL_SIZE, i, i); return false; }
+    if (i + 1 < A.nnz) {
+      const uint4 nx = A.elements[i + 1];
+      if (e.y > nx.y) { log_event(L, ABFT_EV_ROW_ORDER, i, 0); return false; }
+      if (e.y == nx.y && e.x >= nx.x) { log_event(L, ABFT_EV_COL_ORDER, i, i); return false; }
+    }
+    return true;
+  }
+  if (MODE == ABFT_MODE_SED) {
+    if (coo_overall(e)) { log_event(L, ABFT_EV_SED_DETECTED, i, 0); return false; }
+    return true;
+  }
+  if (MODE == ABFT_MODE_SEC7 || MODE == ABFT_MODE_SEC8 || MODE == ABFT_MODE_SECDED) {
+    const uint32_t odd = (MODE == ABFT_MODE_SEC7) ? 0u : coo_overall(e);
+    if (MODE == ABFT_MODE_SEC8 && !odd) return true;  // the syndrome is only looked at when the parity trips
+    const uint32_t s = coo_syndrome(e);
+    const bool repair = (MODE == ABFT_MODE_SEC7) ? (s != 0) : (odd != 0);
+    if (repair) {
+      if (s) {
+        const uint32_t bit = coo_flipped_bit(s);
+        // a multi-bit fault can give bit >= 128, where the reference writes past its element (UB): reported, left alone
+        if (bit < 128) coo_word(e, bit / 32) ^= 1u << (bit % 32);
+        log_event(L, ABFT_EV_CORRECTED_BIT, i, bit);
+      } else {
+        e.x ^= 1u << 24;
+        log_event(L, ABFT_EV_CORRECTED_PARITY, i, 0);
+      }
+      A.elements[i] = e;  // mat->elements[i] = element (COO/CPUContext.cpp:254, 311, 363)
+    } else if (MODE == ABFT_MODE_SECDED && s) {
+      log_event(L, ABFT_EV_DOUBLE_BIT, i, 0);
+      return false;
+    }
+  }
+  return true;
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t coo_out_index(const uint4 &e) {
+  return (MODE >= ABFT_MODE_SED) ? (e.x & 0x00FFFFFFu) : e.x;
+}
+
+__device__ __forceinline__ double coo_value(const uint4 &e) { return __hiloint2double((int)e.w, (int)e.z); }
+
+// result[c] = sum over group c, in element order, of value * vec[row]   (separate multiply and add: no FMA,
+// like the reference build)
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+coo_spmv_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ result, LogRef L) {
+  const uint32_t stride = gridDim.x * kBlock;
+  for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < A.N; c += stride) {
+    double sum = 0.0;
+    const uint32_t kb = A.colptr[c], ke = A.colptr[c + 1];
+    for (uint32_t k = kb; k < ke; k++) {
+      const uint32_t i = A.perm[k];
+      uint4 e = A.elements[i];
+      if (!coo_check<MODE>(e, i, A, L)) continue;  // fatal at this element: the host stops at the first one in index order
+      const uint32_t col = coo_out_index<MODE>(e);
+      if (col != c) {
+        // the element no longer belongs to this output entry: leave it to the fix-up kernel
+        const uint32_t slot = atomicAdd(&A.stray[0], 1u);
+        if (slot < kMaxStray) A.stray[1 + slot] = i;
+        continue;
+      }
+      if (e.y >= A.N) continue;  // vec[] would be read out of bounds (UB in the reference): dropped, as in the oracle
+      sum = __dadd_rn(sum, __dmul_rn(coo_value(e), vec[e.y]));
+    }
+    result[c] = sum;
+  }
+}
+
+// One thread.  For every output entry a stray element now points at: recompute that entry from its own
+// group (minus the members that strayed away) and the strays that target it, in ascending element index.
+// The elements were already checked / repaired by coo_spmv_kernel; nothing is logged here.
+template <int MODE>
+__global__ void coo_stray_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ result) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint32_t n = min(A.stray[0], kMaxStray);
+  A.stray[0] = 0;
+  for (uint32_t s = 0; s < n; s++) {
+    const uint32_t target = coo_out_index<MODE>(A.elements[A.stray[1 + s]]);
+    if (target >= A.N) continue;  // result[] would be written out of bounds (UB in the reference): dropped
+    bool seen = false;            // this target was recomputed for an earlier stray
+    for (uint32_t q = 0; q < s && !seen; q++) seen = coo_out_index<MODE>(A.elements[A.stray[1 + q]]) == target;
+    if (seen) continue;
+    double sum = 0.0;
+    uint32_t k = A.colptr[target];
+    const uint32_t ke = A.colptr[target + 1];
+    uint32_t last = 0;       // strays with an index below `last` have been merged
+    bool first = true;
+    for (;;) {
+      // next candidate from the group (members that still belong to it)
+      uint32_t gi = 0xFFFFFFFFu;
+      while (k < ke) {
+        const uint32_t i = A.perm[k];
+        if (coo_out_index<MODE>(A.elements[i]) == target) { gi = i; break; }
+        k++;
+      }
+      // smallest stray index >= last that targets this entry
+      uint32_t si = 0xFFFFFFFFu;
+      for (uint32_t q = 0; q < n; q++) {
+        const uint32_t i = A.stray[1 + q];
+        if ((first || i >= last) && i < si && coo_out_index<MODE>(A.elements[i]) == target) si = i;
+      }
+      const uint32_t i = min(gi, si);
+      if (i == 0xFFFFFFFFu) break;
+      if (i == gi) k++;
+      const uint4 e = A.elements[i];
+      if (e.y < A.N) sum = __dadd_rn(sum, __dmul_rn(coo_value(e), vec[e.y]));
+      last = i + 1;
+      first = false;
+    }
+    result[target] = sum;
+  }
+}
+
+}  // namespace abft

@@ -241,6 +241,32 @@ uint64_t abft_cuda_launch_count(const abft_ctx *ctx);
 /* tiles of the spmv work decomposition */
 int abft_cuda_matrix_tiles(const abft_matrix *mat);
 
+/* ---------------------------------------------------------------------------
+ * COO format -- the reference's second executable, cg-coo (COO/CPUContext.h:17-22 struct cg_matrix
+ * {N, nnz, coo_element*}; COO/CPUContext.cpp).  Vectors, dot, calc_xr, calc_p and the fault log are the
+ * ones above.  STATUS: compiled, pinned CPU oracle in place (oracle/coo_oracle.c), not yet run on a GPU.
+ * ------------------------------------------------------------------------- */
+typedef struct abft_coo_matrix abft_coo_matrix;
+
+/* CPUContext::create_matrix + generate_ecc_bits (COO/CPUContext.cpp:11-35, 196-199, 230-233, 269-273, 320-324):
+ * deep copy, one 128-bit element {col | check byte, row, value} per triplet in the caller's order.
+ * Modes none .. secded (crc32c has no COO form). */
+abft_coo_matrix *abft_cuda_coo_matrix_create(abft_ctx *ctx, const uint32_t *columns, const uint32_t *rows,
+                                             const double *values, int N, int nnz);
+void abft_cuda_coo_matrix_destroy(abft_ctx *ctx, abft_coo_matrix *mat);
+int abft_cuda_coo_matrix_nnz(const abft_coo_matrix *mat);
+/* copies the nnz 16-byte elements {uint32 col, uint32 row, double value} to the host (tests) */
+int abft_cuda_coo_matrix_read(abft_ctx *ctx, const abft_coo_matrix *mat, void *elements_out);
+/* CPUContext*::spmv (COO/CPUContext.cpp:104-121, 142-194, 201-228, 235-267, 275-318, 326-379):
+ * result[col] += value * vec[row] in element order per output entry; faults go to the context's log
+ * (abft_cuda_poll_events), formatted with abft_cuda_coo_format_event. */
+int abft_cuda_coo_spmv(abft_ctx *ctx, abft_coo_matrix *mat, const abft_vector *vec, abft_vector *result);
+/* the RMW of CPUContext::inject_bitflip (COO/CPUContext.cpp:138): bit 0..127 of element `index`
+ * (0..31 col, 32..63 row, 64..127 value); the plugin draws index and bits with rand() like :125,136 */
+int abft_cuda_coo_flip_bit(abft_ctx *ctx, abft_coo_matrix *mat, int index, int bit);
+/* the reference's COO message texts (its CONSTRAINTS wording differs from the CSR target's) */
+int abft_cuda_coo_format_event(const abft_event *e, char *buf, int buflen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,3 +79,22 @@ def test_plugin_binary_registers_cuda_targets(O):
         assert f"cuda-{m}" in listed
     for m in ["none", "constraints", "sed", "sec7", "sec8", "secded"]:
         assert f"cpu-{m}" in listed      # the reference's own targets are untouched
+
+
+def test_device_side_masks_equal_the_reference_constants(tmp_path):
+    """The kernels derive their Hamming masks at compile time (csrc/ecc.cuh, csrc/coo.cuh): all 21 CSR and all 28
+    COO masks must be the reference's constants (fixtures generated from CSR/ecc.h and COO/ecc.h)."""
+    import shutil
+    import subprocess
+    from conftest import load_golden
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "print_masks")
+    src = os.path.join(ROOT, "tests", "helpers", "print_masks.cu")
+    subprocess.run([nvcc, "-std=c++17", "-O0", "-o", exe, src], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    out = subprocess.run([exe], check=True, stdout=subprocess.PIPE).stdout.decode().split("\n")
+    csr = [[int(x) for x in ln.split()[2:]] for ln in out if ln.startswith("csr")]
+    coo = [[int(x) for x in ln.split()[2:]] for ln in out if ln.startswith("coo")]
+    assert csr == load_golden("ecc_kats.json")["masks"]
+    assert coo == load_golden("coo_golden.json")["ecc"]["masks"]
