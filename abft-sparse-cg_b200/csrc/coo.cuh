@@ -1,9 +1,9 @@
 // coo.cuh -- the COO format of the reference's second executable (cg-coo): 128-bit elements
 // {col, row, value} with the check byte in col bits 24..31 (reference: COO/ecc.h:7-16, COO/CPUContext.cpp).
 //
-// STATUS: written against oracle/coo_oracle.c (which is pinned against the reference), compiled for sm_100a,
-// NOT YET RUN ON A GPU -- the round's GPU budget was spent before this file existed.  Its GPU tests
-// (tests/test_gpu_coo.py) are opt-in (ABFT_COO_GPU_TESTS=1) until they have been seen green on hardware.
+// STATUS: parity green on a B200 against oracle/coo_oracle.c, which is pinned against the reference
+// (tests/test_gpu_coo.py: encoded elements, result[], events, repaired elements bit for bit; CG iteration counts).
+// Correctness first: no TMA staging, no fused dot, not yet profiled or tuned (DESIGN.md 0, row f).
 //
 // The reference's loop is a scatter: for every element in index order, result[col] += value * vec[row]
 // (COO/CPUContext.cpp:104-121).  Each output entry therefore accumulates its elements in ascending element

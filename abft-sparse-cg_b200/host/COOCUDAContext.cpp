@@ -13,7 +13,8 @@
 // (COO/CPUContext.cpp:159,164,177,187,214,256,298,307,350,359,371) and exit(1)s on a fatal one at the
 // first call that needs the spmv's result, before anything else reaches stdout.
 //
-// STATUS: like csrc/coo.cuh -- builds, not yet run on a GPU.  Single GPU (ABFT_CUDA_DEVICE selects it).
+// STATUS: the C ABI underneath is parity green on a B200 (tests/test_gpu_coo.py); this binary (cg-coo-cuda) builds and
+// registers its six targets but has not been driven end to end on a GPU yet.  Single GPU (ABFT_CUDA_DEVICE selects it).
 #include "CGContext.h"  // reference header
 
 #include <cstdio>

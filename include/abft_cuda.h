@@ -244,7 +244,7 @@ int abft_cuda_matrix_tiles(const abft_matrix *mat);
 /* ---------------------------------------------------------------------------
  * COO format -- the reference's second executable, cg-coo (COO/CPUContext.h:17-22 struct cg_matrix
  * {N, nnz, coo_element*}; COO/CPUContext.cpp).  Vectors, dot, calc_xr, calc_p and the fault log are the
- * ones above.  STATUS: compiled, pinned CPU oracle in place (oracle/coo_oracle.c), not yet run on a GPU.
+ * ones above.  STATUS: parity green on a B200 against the pinned COO oracle (tests/test_gpu_coo.py); not yet tuned.
  * ------------------------------------------------------------------------- */
 typedef struct abft_coo_matrix abft_coo_matrix;
 

@@ -1,11 +1,11 @@
 """The LOGIC of the COO kernels (abft-sparse-cg_b200/csrc/coo.cuh), executed on the CPU.
 
-There is no GPU in the build container and round 1's GPU budget was spent before the COO kernels existed, so
-tests/test_gpu_coo.py has not run yet.  Until it has, this is the check those kernels get: the product's own
-kernel source, unmodified, is compiled by g++ against a shim of the CUDA built-ins (tests/helpers/cuda_shim/) and run
-one emulated thread after the other (tests/helpers/coo_emul.cpp), then compared with the COO oracle -- which is
-pinned against the reference (tests/test_oracle_coo.py).  Bit-exact bars, as for the GPU tests.  What this cannot
-see: races, memory ordering, launch configuration, performance.
+There is no GPU in the build container, so the CPU suite checks the COO kernels this way: the product's own kernel
+source, unmodified, is compiled by g++ against a shim of the CUDA built-ins (tests/helpers/cuda_shim/) and run one
+emulated thread after the other (tests/helpers/coo_emul.cpp), then compared with the COO oracle -- which is pinned
+against the reference (tests/test_oracle_coo.py).  Bit-exact bars, as for the GPU tests (tests/test_gpu_coo.py, the
+same cases through the C ABI on a B200).  What this cannot see: races, memory ordering, launch configuration,
+performance.
 """
 import ctypes as C
 import os

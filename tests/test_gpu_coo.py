@@ -1,8 +1,7 @@
 """COO format on the GPU (abft_cuda_coo_*) against the pinned COO oracle (oracle/coo_oracle.c).
 
-OPT-IN: these tests run only with ABFT_COO_GPU_TESTS=1.  The COO kernels (abft-sparse-cg_b200/csrc/coo.cuh) were
-written after round 1's GPU budget was spent: they compile for sm_100a and their oracle is pinned against the
-reference, but they have not been seen green on hardware yet -- so they do not ride along with `pytest -m gpu`.
+All 22 green on a B200 (gpurun_out/pytest_coo*.txt, end of round 1); the same cases also run on the CPU against the
+kernels' own source through a shim of the CUDA built-ins (tests/test_coo_kernel_logic.py).
 
 Bars: bit-exact encoded elements, events (kind, index, bit), repaired elements and result[] (the kernel keeps the
 reference's accumulation order per output entry and uses no FMA); CG iteration counts equal, rr within 1e-10
@@ -14,9 +13,7 @@ import re
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ABFT_COO_GPU_TESTS") != "1",
-                                 reason="COO kernels not yet validated on a GPU (set ABFT_COO_GPU_TESTS=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 RTOL = 1e-10
 MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded"]
