@@ -22,7 +22,7 @@ SYMBOLS = [
     "abft_cuda_ctx_create", "abft_cuda_ctx_destroy", "abft_cuda_ctx_mode", "abft_cuda_ctx_sync",
     "abft_cuda_ctx_stream",
     "abft_cuda_matrix_create", "abft_cuda_matrix_create_part", "abft_cuda_matrix_destroy",
-    "abft_cuda_matrix_rows", "abft_cuda_matrix_nnz", "abft_cuda_matrix_read", "abft_cuda_matrix_poke_rowptr",
+    "abft_cuda_plan_tiles", "abft_cuda_matrix_rows", "abft_cuda_matrix_nnz", "abft_cuda_matrix_read", "abft_cuda_matrix_poke_rowptr",
     "abft_cuda_matrix_poke_col", "abft_cuda_matrix_poke_value",
     "abft_cuda_vector_create", "abft_cuda_vector_wrap", "abft_cuda_vector_view", "abft_cuda_vector_destroy",
     "abft_cuda_vector_len", "abft_cuda_vector_dev_ptr", "abft_cuda_vector_map", "abft_cuda_vector_unmap",
@@ -85,6 +85,7 @@ def load():
     sig("abft_cuda_matrix_create", vp, vp, vp, vp, vp, i32, i32)
     sig("abft_cuda_matrix_create_part", vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_int64)
     sig("abft_cuda_matrix_destroy", None, vp, vp)
+    sig("abft_cuda_plan_tiles", i32, vp, i32, i32, vp, i32)
     sig("abft_cuda_matrix_rows", i32, vp)
     sig("abft_cuda_matrix_nnz", i32, vp)
     sig("abft_cuda_matrix_tiles", i32, vp)

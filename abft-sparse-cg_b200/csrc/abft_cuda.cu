@@ -300,6 +300,30 @@ static void build_tiles(const uint32_t *rowptr, uint32_t n_rows, uint32_t tile_n
   }
 }
 
+// The spmv work decomposition of a CSR structure, without a device: what create_matrix would build for these row
+// pointers (host logic only; used by the CPU tests and by integrators who want to see how a matrix will be cut).
+// tile_nnz <= 0: the size create_matrix picks (2048, or 1536 if that cut has irregular tiles).  Writes up to `cap`
+// records {row_begin, nnz_begin, nnz_end, info} and returns the number of tiles (which may exceed cap).
+int abft_cuda_plan_tiles(const uint32_t *rowptr, int n_rows, int tile_nnz, uint32_t *out, int cap) {
+  if (!rowptr || n_rows < 0) return fail(-1, "bad arguments to plan_tiles", __FILE__, __LINE__);
+  std::vector<Tile> tiles;
+  if (tile_nnz > 0) {
+    build_tiles(rowptr, (uint32_t)n_rows, (uint32_t)tile_nnz, tiles);
+  } else {
+    build_tiles(rowptr, (uint32_t)n_rows, (uint32_t)kTileNnz, tiles);
+    bool irregular = false;
+    for (const Tile &t : tiles) irregular |= !(t.info & kTileRegular);
+    if (irregular) build_tiles(rowptr, (uint32_t)n_rows, (uint32_t)kTileNnzDyn, tiles);
+  }
+  for (size_t i = 0; i < tiles.size() && (int)i < cap && out; i++) {
+    out[4 * i + 0] = tiles[i].row_begin;
+    out[4 * i + 1] = tiles[i].nnz_begin;
+    out[4 * i + 2] = tiles[i].nnz_end;
+    out[4 * i + 3] = tiles[i].info;
+  }
+  return (int)tiles.size();
+}
+
 abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, const uint32_t *rows,
                                           const double *values, int n_rows, int nnz, int N_global, int row_offset,
                                           int64_t nnz_offset) {

@@ -103,6 +103,11 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *ctx, const uint32_t *columns
                                           const double *values, int n_rows, int nnz, int N_global,
                                           int row_offset, int64_t nnz_offset);
 void abft_cuda_matrix_destroy(abft_ctx *ctx, abft_matrix *mat);
+/* Host-only: the spmv work decomposition ("tiles": runs of whole rows) create_matrix would build for
+ * these CSR row pointers.  tile_nnz <= 0: the size create_matrix picks.  Writes up to cap records
+ * {row_begin, nnz_begin, nnz_end, info} (info: bits 0..15 rows, bit 16 thread-per-row tile, bit 17 single row longer
+ * than a tile, bits 18..29 longest row) and returns the number of tiles.  Needs no device. */
+int abft_cuda_plan_tiles(const uint32_t *rowptr, int n_rows, int tile_nnz, uint32_t *out, int cap);
 int abft_cuda_matrix_rows(const abft_matrix *mat);
 int abft_cuda_matrix_nnz(const abft_matrix *mat);
 /* copy the stored (encoded) CSR arrays back; any pointer may be NULL.
