@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1 << 21)
     ap.add_argument("--nnz", type=int, default=50_000_000)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--format", default="csr", choices=["csr", "coo"], help="coo: abft_cuda_coo_spmv (DESIGN.md 9)")
     ap.add_argument("--warm", type=int, default=300)
     a = ap.parse_args()
     import torch
@@ -43,28 +44,32 @@ def main():
     vec = np.random.default_rng(1).random(t.N)
     want = sp.csr_matrix((t.vals, (t.rows, t.cols)), shape=(t.N, t.N)) @ vec
     _, b_spmv = bench.alg_bytes(t.N, nnz)
+    coo = a.format == "coo"
+    if coo:
+        b_spmv = 16 * nnz + 16 * t.N   # elements once, vec read once, result written once
     for mode in a.modes.split(","):
         ctx = pkg.CUDAContext(mode, 0)
-        A = ctx.create_matrix(t.cols, t.rows, t.vals, t.N)
+        A = ctx.create_coo_matrix(t.cols, t.rows, t.vals, t.N) if coo else ctx.create_matrix(t.cols, t.rows, t.vals, t.N)
+        spmv = ctx.coo_spmv if coo else ctx.spmv
         p, w = ctx.create_vector(t.N), ctx.create_vector(t.N)
         ctx.upload(p, vec)
         stream = torch.cuda.ExternalStream(ctx.L.abft_cuda_ctx_stream(ctx.ctx))
         for _ in range(a.warm):          # long enough for the clocks to settle
-            ctx.spmv(A, p, w)
+            spmv(A, p, w)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
         for _ in range(a.reps):
-            ctx.spmv(A, p, w)
+            spmv(A, p, w)
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
         got = ctx.download(w)
         err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
         print(json.dumps({"tag": a.tag, "lib": os.path.basename(os.environ.get("ABFT_CUDA_LIB", "libabftcuda.so")),
-                          "workload": a.workload, "mode": mode, "N": t.N, "nnz": nnz, "ms": round(ms, 4),
+                          "workload": a.workload, "format": a.format, "mode": mode, "N": t.N, "nnz": nnz, "ms": round(ms, 4),
                           "GBs": round(b_spmv / ms / 1e6, 1), "frac": round(b_spmv / ms / 1e6 / 6537.0, 3),
-                          "tiles": int(ctx.L.abft_cuda_matrix_tiles(A.handle)), "max_rel_err": err,
+                          "tiles": (0 if coo else int(ctx.L.abft_cuda_matrix_tiles(A.handle))), "max_rel_err": err,
                           "events": len(ctx.messages)}), flush=True)
         ctx.close()
 
