@@ -472,6 +472,14 @@ def main():
             "clocks": clocks,
             "setup": {"generate_s": t_gen, "create_matrix_s": t_upload}}
 
+    if args.workload == "powerlaw":
+        # random columns: every non-zero is one 32-byte sector request for 8 useful bytes, and the B200 serves one such
+        # request per clock per SM (tools/gather_bench.cu, profiles/r1_gather_bench.txt: 288 G/s from an L2-resident
+        # vector) -- that, not HBM, is this workload's ceiling
+        gathers = nnz_local / (ms_spmv * 1e-3) / 1e9
+        line["gather_rate"] = {"achieved": gathers, "peak": 288.0, "unit": "G gathers/s", "frac": gathers / 288.0,
+                               "peak_source": "measured: profiles/r1_gather_bench.txt (1 sector per clock per SM)"}
+
     if world == 1 and rank == 0:
         # ---- every ABFT mode, briefly ----
         if args.all_modes:
