@@ -94,14 +94,61 @@ def powerlaw(N: int, target_nnz: int, alpha: float = 2.0, max_deg: int = 4096, s
     deg = np.minimum(np.minimum(deg, max_deg), np.arange(N, dtype=np.int64))
     rows_l = np.repeat(np.arange(N, dtype=np.int64), deg)
     cols_l = (rng.random(rows_l.shape[0]) * rows_l).astype(np.int64)          # j in [0, i)
-    key = np.unique(rows_l * N + cols_l)                                      # distinct, sorted
+    key = rows_l * N + cols_l
+    key.sort()                                                                # (np.unique is 70x slower here)
+    if key.shape[0]:
+        keep = np.empty(key.shape, dtype=bool)
+        keep[0] = True
+        np.not_equal(key[1:], key[:-1], out=keep[1:])
+        key = key[keep]                                                       # distinct, sorted
     rows_l, cols_l = key // N, key % N
-    rdeg = np.bincount(rows_l, minlength=N) + np.bincount(cols_l, minlength=N)
-    r = np.concatenate([rows_l, cols_l, np.arange(N, dtype=np.int64)])
-    c = np.concatenate([cols_l, rows_l, np.arange(N, dtype=np.int64)])
-    v = np.concatenate([np.full(2 * rows_l.shape[0], -1.0), rdeg.astype(np.float64) + 1.0])
-    order = np.argsort(r * N + c, kind="stable")
-    return Triplets(c[order], r[order], v[order], N)
+    del key
+    return _mirror_lower(rows_l, cols_l, N)
+
+
+def _mirror_lower(rows_l, cols_l, N) -> Triplets:
+    """Strict lower triangle (sorted by (row, col)) -> the full symmetric matrix, sorted by (row, col), without a
+    sort of the mirrored entries: row i of the result is [row i of L | diagonal | row i of L^T], and the transpose
+    is a counting sort (a 2e8-entry argsort takes minutes; this takes seconds)."""
+    n_l = rows_l.shape[0]
+    cnt_l = np.bincount(rows_l, minlength=N)            # entries left of the diagonal
+    cnt_u = np.bincount(cols_l, minlength=N)            # entries right of it
+    # transpose of L by a stable counting sort on the column: within a column the rows stay ascending
+    t_order = np.argsort(cols_l, kind="stable") if n_l < (1 << 16) else _stable_counting_order(cols_l, cnt_u, N)
+    ptr = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(cnt_l + cnt_u + 1, out=ptr[1:])
+    start_l = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(cnt_l, out=start_l[1:])
+    start_u = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(cnt_u, out=start_u[1:])
+    nnz = int(ptr[-1])
+    c = np.empty(nnz, dtype=np.uint32)
+    r = np.empty(nnz, dtype=np.uint32)
+    v = np.empty(nnz, dtype=np.float64)
+    r[:] = np.repeat(np.arange(N, dtype=np.uint32), cnt_l + cnt_u + 1)
+    v[:] = -1.0
+    # lower part of row i sits at ptr[i] + (k - start_l[i]) for the row's k-th entry of L
+    pos = np.arange(n_l, dtype=np.int64) + np.repeat(ptr[:-1] - start_l[:-1], cnt_l)
+    c[pos] = cols_l
+    # diagonal
+    dpos = ptr[:-1] + cnt_l
+    c[dpos] = np.arange(N, dtype=np.uint32)
+    v[dpos] = (cnt_l + cnt_u).astype(np.float64) + 1.0
+    # upper part: row i = column i of L, entries (their rows) ascending
+    pos = np.arange(n_l, dtype=np.int64) + np.repeat(dpos + 1 - start_u[:-1], cnt_u)
+    c[pos] = rows_l[t_order]
+    return Triplets(c, r, v, N)
+
+
+def _stable_counting_order(keys, counts, N):
+    """argsort(keys, kind='stable') for integer keys in [0, N) with known counts, through scipy's O(nnz) CSR->CSC
+    conversion (a counting sort in C)."""
+    import scipy.sparse as sp
+    n = keys.shape[0]
+    # one entry per element: row = its position's "chunk" does not matter; use a 1 x n trick: matrix with
+    # rows = key, cols = position is already "sorted by position within a key" after tocsr()
+    m = sp.coo_matrix((np.ones(n, dtype=np.int8), (keys, np.arange(n, dtype=np.int64))), shape=(N, n)).tocsr()
+    return m.indices.astype(np.int64)
 
 
 def write_mtx(path: str, t: Triplets) -> None:

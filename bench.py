@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--workload", default="poisson3d", choices=["poisson3d", "poisson2d_blocks", "powerlaw"],
                     help="poisson3d: grid^3 7-point (default, BASELINE configs[2]); poisson2d_blocks: 512^2 5-point x 64 "
                          "diagonal blocks (largest 5-point case the 24-bit column allows, configs[3]); powerlaw: irregular "
-                         "rows, N=2^21, ~5e7 nnz (configs[4], scaled)")
+                         "rows, --rows x --nnz (default N=2^23, ~2e8 nnz: configs[4] as named; round 1 measured 2^21 / 5e7)")
+    ap.add_argument("--rows", type=int, default=1 << 23, help="powerlaw: N (<= 2^24 for the ECC modes)")
+    ap.add_argument("--nnz", type=int, default=200_000_000, help="powerlaw: target non-zeros after mirroring")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--all-modes", type=int, default=1, help="also time every ABFT mode briefly (N=1 only)")
     ap.add_argument("--cpu-iters", type=int, default=5, help="iterations of the CPU baseline sample")
@@ -224,7 +226,7 @@ def main():
         nnz = 7 * N - 6 * n * n
         workload = f"poisson3d_{n} (3D 7-point Poisson {n}^3: N={N}, nnz={nnz}), mode {args.mode}, -c 0 -i K"
     else:
-        full = mg.poisson2d(512, 64) if args.workload == "poisson2d_blocks" else mg.powerlaw(1 << 21, 50_000_000, seed=1)
+        full = mg.poisson2d(512, 64) if args.workload == "poisson2d_blocks" else mg.powerlaw(args.rows, args.nnz, seed=1)
         N, nnz = full.N, full.nnz
         what = ("2D 5-point Poisson 512^2 replicated -b 64" if args.workload == "poisson2d_blocks"
                 else "power-law row lengths (Zipf 2.0, <= 4096 per row), SPD")

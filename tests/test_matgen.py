@@ -55,3 +55,19 @@ def test_mtx_roundtrip_through_reference_loader(pkg, O, tmp_path):
     assert f"number of non-zeros   = {t3.nnz} " in text
     res = O.OracleMatrix("secded", t3.cols, t3.rows, t3.vals, t3.N).cg(pkg.matgen.rhs(t3.N), 1000, 1e-10)
     assert f"ran for {res['iterations']} iterations" in text
+
+
+@pytest.mark.parametrize("N,nnz", [(1, 1), (2, 4), (50, 300), (2000, 40000), (40000, 600000)])
+def test_powerlaw_mirror_equals_a_plain_sort(pkg, N, nnz):
+    """The sort-free assembly (row = [L row | diagonal | L^T row], counting-sort transpose; the larger case takes the
+    scipy path) gives exactly what sorting the mirrored triplets gives."""
+    t = pkg.matgen.powerlaw(N, nnz, seed=4)
+    low = t.cols < t.rows
+    rl, cl = t.rows[low].astype(np.int64), t.cols[low].astype(np.int64)
+    deg = np.bincount(rl, minlength=N) + np.bincount(cl, minlength=N)
+    r = np.concatenate([rl, cl, np.arange(N)])
+    c = np.concatenate([cl, rl, np.arange(N)])
+    v = np.concatenate([np.full(2 * rl.shape[0], -1.0), deg + 1.0])
+    order = np.argsort(r * N + c, kind="stable")
+    assert np.array_equal(t.rows, r[order]) and np.array_equal(t.cols, c[order]) and np.array_equal(t.vals, v[order])
+    assert t.nnz == 2 * rl.shape[0] + N
