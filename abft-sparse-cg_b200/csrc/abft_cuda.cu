@@ -212,6 +212,14 @@ abft_ctx *abft_cuda_ctx_create(int mode, int device) {
   }
   CKP(cudaSetDevice(device));
   abft_ctx *c = new abft_ctx();
+  // every early `return nullptr` below releases what was allocated so far
+  struct Cleanup {
+    abft_ctx *c;
+    bool armed = true;
+    ~Cleanup() {
+      if (armed) abft_cuda_ctx_destroy(c);
+    }
+  } cleanup{c};
   c->mode = mode;
   c->device = device;
   cudaDeviceProp prop;
@@ -235,22 +243,23 @@ abft_ctx *abft_cuda_ctx_create(int mode, int device) {
   memset(c->h_loop, 0, sizeof(int) * 4);
   if (ensure_tables(device) != 0) return nullptr;
   CKP(cudaDeviceSynchronize());
+  cleanup.armed = false;
   return c;
 }
 
 void abft_cuda_ctx_destroy(abft_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_log);
-  cudaFreeHost(c->h_flag);
+  if (c->h_flag) cudaFreeHost(c->h_flag);
   cudaFree(c->d_scalars);
-  cudaFreeHost(c->h_scalars);
+  if (c->h_scalars) cudaFreeHost(c->h_scalars);
   cudaFree(c->d_partials);
   cudaFree(c->d_counter);
   cudaFree(c->d_loop);
-  cudaFreeHost(c->h_loop);
-  cudaStreamDestroy(c->stream);
+  if (c->h_loop) cudaFreeHost(c->h_loop);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
@@ -522,8 +531,14 @@ abft_vector *abft_cuda_vector_create(abft_ctx *c, int N) {
   abft_vector *v = new abft_vector();
   v->N = N;
   v->owns = true;
-  CKP(cudaMalloc(&v->d, sizeof(double) * (size_t)std::max(N, 1)));
-  CKP(cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)std::max(N, 1), c->stream));
+  cudaError_t e = cudaMalloc(&v->d, sizeof(double) * (size_t)std::max(N, 1));
+  if (e == cudaSuccess) e = cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)std::max(N, 1), c->stream);
+  if (e != cudaSuccess) {
+    fail((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    cudaFree(v->d);
+    delete v;
+    return nullptr;
+  }
   return v;
 }
 
@@ -851,9 +866,15 @@ abft_comm *abft_cuda_comm_create(abft_ctx *c, int rank, int world) {
   abft_comm *m = new abft_comm();
   m->rank = rank;
   m->world = world;
-  CKP(cudaMalloc(&m->win[rank], sizeof(CommWindow)));
-  CKP(cudaMemset(m->win[rank], 0, sizeof(CommWindow)));
-  CKP(cudaDeviceSynchronize());
+  cudaError_t e = cudaMalloc(&m->win[rank], sizeof(CommWindow));
+  if (e == cudaSuccess) e = cudaMemset(m->win[rank], 0, sizeof(CommWindow));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    fail((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    cudaFree(m->win[rank]);
+    delete m;
+    return nullptr;
+  }
   return m;
 }
 
