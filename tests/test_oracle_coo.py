@@ -189,3 +189,21 @@ def test_live_reference_random_matrices_and_flips(CO, pkg):
             assert not fatal and [CO.format_event(*e) for e in ev] == text.splitlines()
             assert np.array_equal(y.view(np.uint64), y_ref.view(np.uint64))
             assert np.array_equal(m.elements.view(np.uint32), rc.elements.view(np.uint32))
+
+
+def test_differential_fuzz_against_the_reference_coo(CO):
+    """tools/fuzz_oracle_vs_ref.py --format coo: random matrices x modes x 1..3 flips (any of the 128 bits) in each of
+    1..2 elements, the reference's cg-coo target in a forked child (it exit(1)s on fatal faults): same lines, same exit
+    status, same repaired elements, same result[] wherever the reference's behaviour is defined."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if not CO.have_ref():
+        pytest.skip("oracle/_ref/libref_coo.so not built (no reference tree here)")
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_oracle_vs_ref.py")
+    out = subprocess.run([sys.executable, tool, "--format", "coo", "--trials", "400", "--seed", "20261018"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    stats = json.loads(out.stdout.strip().splitlines()[-1])
+    assert stats["trials"] == 400 and stats["fatal"] > 20 and stats["corrected"] > 40 and stats["result_compared"] > 100

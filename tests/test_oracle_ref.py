@@ -82,3 +82,21 @@ def test_vector_kernels_bit_identical(ref, pkg):
     rc.calc_p(vp, vr, -1.25)
     L.orc_calc_p(p2, r2, -1.25, N)
     assert np.array_equal(rc.view(vp), p2)
+
+
+def test_differential_fuzz_against_the_reference(ref):
+    """Random matrices x modes x multi-bit / multi-element faults (and row-pointer faults under `constraints`), one spmv
+    each, the reference's side in a forked child because it exit(1)s on fatal faults: same lines, same exit status,
+    same repaired matrix, same result[] wherever the reference's behaviour is defined (tools/fuzz_oracle_vs_ref.py).
+    Run as its own process: it pins OpenMP to one thread before libgomp loads (serial message order; and a child
+    forked from a process whose OpenMP pool already exists would hang in the reference's parallel loop)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_oracle_vs_ref.py")
+    out = subprocess.run([sys.executable, tool, "--trials", "400", "--seed", "20261018"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    stats = json.loads(out.stdout.strip().splitlines()[-1])
+    assert stats["trials"] == 400 and stats["fatal"] > 50 and stats["corrected"] > 50 and stats["result_compared"] > 100
