@@ -49,10 +49,12 @@ def test_random_faults_gpu_equals_oracle(pkg, O, mode):
         events, fatal = ctx.poll_events()
         what = (mode, trial, flips, pokes)
         assert (fatal, events) == (fatal0, ev0), what
-        cols, rows, vals = ctx.read_matrix(A)
-        assert np.array_equal(cols, om.cols) and np.array_equal(vals.view(np.uint64), om.values.view(np.uint64)), what
-        assert np.array_equal(rows, om.rows), what
         if not fatal:
+            # (after a fatal fault the reference has exited; rows behind it were never visited there, while the
+            # device has walked -- and possibly repaired -- all of them: nothing to compare)
+            cols, rows, vals = ctx.read_matrix(A)
+            assert np.array_equal(cols, om.cols) and np.array_equal(vals.view(np.uint64), om.values.view(np.uint64)), what
+            assert np.array_equal(rows, om.rows), what
             assert np.array_equal(ctx.download(w).view(np.uint64), y0.view(np.uint64)), what
         fatal_seen += fatal
         repaired_seen += bool(events) and not fatal
