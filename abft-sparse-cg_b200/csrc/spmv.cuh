@@ -37,7 +37,10 @@
 
 namespace abft {
 
-constexpr int kTileNnz = 2048;
+#ifndef ABFT_TILE_STATIC
+#define ABFT_TILE_STATIC 2048
+#endif
+constexpr int kTileNnz = ABFT_TILE_STATIC;  // (knob for experiments; 2048 is what round 1 measured)
 // Matrices with irregular tiles (dynamic schedule) are gather-bound, and a gather in flight holds an L1 line: with
 // 4 CTAs x 52 KB of stage buffers the SM's 256 KB are all shared memory and the ~28 KB of L1 left cap the gathers in
 // flight (measured: same kernel, carveout forced down to 164 KB / 3 CTAs: 0.41 -> 0.32 ms).  Their tiles are smaller,
@@ -303,6 +306,16 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
     ok[k] = ((uint32_t)k < count);
     xv[k] = __ldg(x + min(col, n_cols - 1u));
   }
+#if ABFT_WALK_UNIFORM
+  // experiment (opt-in): when every lane that is here has a full chunk -- interior rows of a stencil --
+  // the adds need no predicate (the predicated form costs an ISETP and two FSEL per element).  The vote only picks
+  // the code path; each lane's own count still decides what is correct for it.
+  if (__all_sync(__activemask(), count >= (uint32_t)LEN)) {
+#pragma unroll
+    for (int k = 0; k < LEN; k++) sum = __dadd_rn(sum, __dmul_rn(v[k], xv[k]));
+    return sum;
+  }
+#endif
 #pragma unroll
   for (int k = 0; k < LEN; k++) {
     // predicated add (not a select between sum and sum + prod: that costs two FSEL per element)
@@ -340,6 +353,9 @@ struct WaitSpec {
   unsigned int mask;     // ... for every rank s in this mask (0: single GPU, no wait)
 };
 
+#ifndef ABFT_WALK_UNIFORM
+#define ABFT_WALK_UNIFORM 0
+#endif
 #ifndef ABFT_SPMV_MINB
 #define ABFT_SPMV_MINB 4  // resident CTAs per SM the register allocation is tuned for
 #endif

@@ -32,6 +32,10 @@ static inline uint32_t __brev(uint32_t x) {
   return r;
 }
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {
+  s &= 31u;
+  return s ? (hi << s) | (lo >> (32u - s)) : hi;
+}
 static inline double __dadd_rn(double a, double b) { return a + b; }   // built with -ffp-contract=off
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline int __double2loint(double v) { uint64_t b; memcpy(&b, &v, 8); return (int)(uint32_t)b; }
