@@ -633,6 +633,15 @@ static int spmv_resident_ctas(abft_ctx *c) {
       cudaFuncSetAttribute(spmv_kernel<MODE, DYN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            std::min(100, (need_kb * 100 + 227) / 228));
     }
+    if (!DYN) {
+      // experiment knob (tools/ab_variants.sh): shared-memory carveout of the static kernel in
+      // percent, to leave the gathers more L1 when the tiles are smaller than the default.  Unset: the driver's choice.
+      const char *e = getenv("ABFT_CUDA_STATIC_CARVEOUT");
+      if (e && *e) {
+        const int pct = std::max(0, std::min(100, atoi(e)));
+        cudaFuncSetAttribute(spmv_kernel<MODE, DYN>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      }
+    }
     cached = per_sm;
   }
   return cached * c->num_sms;
