@@ -102,6 +102,7 @@ struct SpmvCfg {
 };
 
 // ---- PTX: mbarrier + TMA bulk copy (global -> shared) -------------------------------
+#ifndef ABFT_HOST_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -141,6 +142,28 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// sum += prod if ok: a predicated add (not a select between sum and sum + prod: that costs two FSEL per element)
+__device__ __forceinline__ double add_if(double sum, double prod, bool ok) {
+  asm("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p add.rn.f64 %0, %0, %1;\n}" : "+d"(sum) : "d"(prod), "r"((uint32_t)ok));
+  return sum;
+}
+#else
+// Host emulation (tests/helpers/cuda_shim_mt/, test infrastructure): the same contracts in plain C++, so that the
+// kernel below can run as 256 CPU threads against the oracle.  Never compiled by nvcc.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { emu::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { emu::mbar_arrive(bar); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
+__device__ __forceinline__ uint64_t l2_evict_first_policy() { return 0; }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t) {
+  emu::bulk_g2s(dst, src, bytes, bar);
+}
+__device__ __forceinline__ void fence_mbarrier_init() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ double add_if(double sum, double prod, bool ok) { return ok ? __dadd_rn(sum, prod) : sum; }
+#endif
 
 __device__ __forceinline__ void split_value(double v, uint32_t &w0, uint32_t &w1) {
   w0 = (uint32_t)__double2loint(v);
@@ -277,7 +300,7 @@ __device__ __forceinline__ void batch_products(const uint32_t (&li)[U], const ui
 template <int MODE, int LEN>
 __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_t count, const uint32_t *s_cols,
                                              const double *s_vals, uint32_t n_cols, const double *__restrict__ x,
-                                             uint32_t &suspect) {
+                                             uint32_t &suspect, bool full = false) {
   uint32_t c[LEN + 1];
   double v[LEN], xv[LEN];
   bool ok[LEN];
@@ -307,21 +330,17 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
     xv[k] = __ldg(x + min(col, n_cols - 1u));
   }
 #if ABFT_WALK_UNIFORM
-  // experiment (opt-in): when every lane that is here has a full chunk -- interior rows of a stencil --
-  // the adds need no predicate (the predicated form costs an ISETP and two FSEL per element).  The vote only picks
-  // the code path; each lane's own count still decides what is correct for it.
-  if (__all_sync(__activemask(), count >= (uint32_t)LEN)) {
+  // experiment (opt-in): when every row of the warp fills the chunk -- interior rows of a stencil --
+  // the adds need no predicate (the predicated form costs an ISETP and two FSEL per element).  `full` is a
+  // warp-uniform vote taken by the caller; it only picks the code path.
+  if (full) {
 #pragma unroll
     for (int k = 0; k < LEN; k++) sum = __dadd_rn(sum, __dmul_rn(v[k], xv[k]));
     return sum;
   }
 #endif
 #pragma unroll
-  for (int k = 0; k < LEN; k++) {
-    // predicated add (not a select between sum and sum + prod: that costs two FSEL per element)
-    const double prod = __dmul_rn(v[k], xv[k]);
-    asm("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p add.rn.f64 %0, %0, %1;\n}" : "+d"(sum) : "d"(prod), "r"((uint32_t)ok[k]));
-  }
+  for (int k = 0; k < LEN; k++) sum = add_if(sum, __dmul_rn(v[k], xv[k]), ok[k]);
   return sum;
 }
 
@@ -365,7 +384,11 @@ template <int MODE, bool DYN>
 __global__ void __launch_bounds__(kBlock, (MODE == ABFT_MODE_CRC32C) ? 3 : ABFT_SPMV_MINB)
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
             const int *__restrict__ active, WaitSpec wait) {
+#ifndef ABFT_HOST_EMU
   extern __shared__ __align__(128) unsigned char dyn_smem[];
+#else
+  unsigned char *const dyn_smem = emu::g_dyn_smem;
+#endif
   using StageBuf = typename SpmvCfg<DYN>::Stage;
   constexpr size_t kSpmvDynSmem = SpmvCfg<DYN>::dyn_smem;
   StageBuf *stage = reinterpret_cast<StageBuf *>(dyn_smem);
@@ -404,10 +427,10 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   }
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&s_full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbarrier_init();
   }
   __syncthreads();
-  if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid == 0) fence_proxy_async();
   if (MODE == ABFT_MODE_CRC32C)
     for (int i = tid; i < 1024; i += kBlock) s_crc[i] = g_crc_tab[i];
   __syncthreads();
@@ -427,7 +450,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
       cbytes = ((t.nnz_end + kOverrun + 3) & ~3u) * 4u - cb * 4u;
       vbytes = ((t.nnz_end + kOverrun + 1) & ~1u) * 8u - vb * 8u;
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_proxy_async();
     mbar_expect_tx(&s_full[s], rbytes + cbytes + vbytes);
     bulk_g2s(B.rptr, A.rowptr + rb, rbytes, &s_full[s], stream_policy);
     if (cbytes) {
@@ -499,7 +522,28 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
       // ---------------- one long row: stream it from global memory in chunks ----------------
       double acc = 0.0;
       bool flagged = false;
-      for (uint32_t base = tid; base < n; base += kLongBatch * kBlock) {
+      // CONSTRAINTS looks at the row's own pointers (staged with the tile), like the reference (CSR/CPUContext.cpp:
+      // 173-182): the tile's range is what they were at create_matrix.  If they have moved, thread 0 does the
+      // reference's row checks and, when they pass, its walk over [start, end) from global memory -- one by one,
+      // in its order (rare: a corrupted rows[]).  Uniform over the CTA (every thread reads the same two words).
+      bool moved = false;
+      if (MODE == ABFT_MODE_CONSTRAINTS) {
+        const uint32_t prs = B.rptr[t.row_begin - rb], pre = B.rptr[t.row_begin + 1 - rb];
+        moved = prs != t.nnz_begin || pre != t.nnz_end;
+        if (moved && tid == 0) {
+          const uint32_t grow = A.row_offset + t.row_begin;
+          if (pre > A.nnz) log_event(L, ABFT_EV_ROW_SIZE, grow, 0);
+          else if (pre < prs) log_event(L, ABFT_EV_ROW_ORDER, grow, 0);
+          else
+            for (uint32_t i = prs; i < pre; i++) {
+              const uint32_t col = A.cols[i];
+              if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, grow); break; }
+              if (i < pre - 1 && A.cols[i + 1] <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, grow); break; }
+              acc = __dadd_rn(acc, __dmul_rn(A.values[i], __ldg(x + col)));
+            }
+        }
+      }
+      for (uint32_t base = tid; !moved && base < n; base += kLongBatch * kBlock) {
         uint32_t li[kLongBatch], cw[kLongBatch];
         double val[kLongBatch], pr[kLongBatch];
         bool ok[kLongBatch];
@@ -569,6 +613,24 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           }
         return sum;
       };
+      bool full_rows = false;
+#if ABFT_WALK_UNIFORM
+      if (!irregular && MODE != ABFT_MODE_CRC32C) {  // (uniform over the CTA)
+        // does every row of this warp fill the unrolled walk?  Lanes without a row do not veto.
+        const uint32_t ml = (t.info >> kTileMaxLenShift) & 0xFFFu;
+        const uint32_t need = ml <= 4 ? 4u : ml;
+        bool mine = true;
+        if (has_row) {
+          uint32_t a = B.rptr[row - rb], b = B.rptr[row + 1 - rb];
+          if (MODE != ABFT_MODE_CONSTRAINTS) {  // the same clamp as the walk below
+            a = min(max(a, t.nnz_begin), t.nnz_end);
+            b = min(max(b, a), t.nnz_end);
+          }
+          mine = b >= a && b - a >= need;
+        }
+        full_rows = __all_sync(0xffffffffu, mine) && ml <= 7;
+      }
+#endif
       if (irregular) {
         // ---------------- irregular tile ----------------
         // The tile's rows are dealt to the warps in equal runs of consecutive rows (warp w owns rows
@@ -684,10 +746,10 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           const uint32_t *sc = B.cols + (rs - cb);
           const double *sv = B.vals + (rs - vb);
           uint32_t suspect = 0;
-          if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
-          else if (max_len == 5) sum = walk_chunk<MODE, 5>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
-          else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
-          else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect);
+          if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
+          else if (max_len == 5) sum = walk_chunk<MODE, 5>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
+          else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
+          else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
           else
             // longer rows: chunks of 4 up to this row's own length (never more than 3 slots past its end,
             // which the over-staged window covers; the trip count may differ between lanes)

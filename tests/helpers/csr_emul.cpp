@@ -1,0 +1,170 @@
+// csr_emul.cpp -- runs the CSR kernels of csrc/{spmv,encode,vecops}.cuh on the CPU, every CTA as 256 real threads
+// (test infrastructure; built by tests/test_csr_kernel_logic.py with g++ -std=c++20 and the shim in
+// tests/helpers/cuda_shim_mt/).  The kernels are the product's own source; only the CUDA built-ins and, under
+// ABFT_HOST_EMU, the PTX helpers of spmv.cuh (mbarrier, bulk copy, fences, the predicated add) are replaced.
+#include "cuda_runtime.h"  // the shim (found first on the include path)
+
+#include <vector>
+
+#include "../../abft-sparse-cg_b200/csrc/encode.cuh"
+#include "../../abft-sparse-cg_b200/csrc/vecops.cuh"
+
+using namespace abft;
+
+namespace {
+struct Emu {
+  int mode = 0;
+  uint32_t n_rows = 0, n_cols = 0, nnz = 0;
+  std::vector<uint32_t> cols, rowptr;  // padded like abft_cuda_matrix_create pads the device arrays
+  std::vector<double> vals;
+  std::vector<Tile> tiles;
+  bool dyn = false;
+  unsigned int tile_counter = 0;
+  DevLog log;
+  unsigned int flag = 0;
+  std::vector<double> partials;
+  unsigned int counter = 0;
+  double scal_dev = 0.0, scal_host = 0.0;
+  unsigned char *smem = nullptr;
+  int grid = 3;  // few CTAs: each takes several tiles (exercises the stage ring and the grid stride)
+};
+
+ReduceOut reduce_of(Emu *e) {
+  ReduceOut r{};
+  r.partials = e->partials.data();
+  r.counter = &e->counter;
+  r.dev = &e->scal_dev;
+  r.host = &e->scal_host;
+  return r;
+}
+
+void fill_crc_tables() {
+  for (int s = 0; s < 4; s++)
+    for (uint32_t i = 0; i < 256; i++) g_crc_tab[s * 256 + i] = crc32c_table_entry(i, s);
+}
+
+template <int MODE, bool DYN>
+void spmv_inst(Emu *e, const double *vec, double *result) {
+  MatView A{};
+  A.rowptr = e->rowptr.data();
+  A.cols = e->cols.data();
+  A.values = e->vals.data();
+  A.tiles = e->tiles.data();
+  A.tile_counter = DYN ? &e->tile_counter : nullptr;
+  A.n_tiles = (uint32_t)e->tiles.size();
+  A.n_rows = e->n_rows;
+  A.nnz = e->nnz;
+  A.n_cols = e->n_cols;
+  A.row_offset = 0;
+  A.nnz_offset = 0;
+  LogRef L{&e->log, &e->flag};
+  const ReduceOut red = reduce_of(e);
+  const int grid = std::max(1, std::min((int)e->tiles.size(), e->grid));
+  emu::launch(grid, kBlock, [&] { spmv_kernel<MODE, DYN>(A, vec, result, L, red, nullptr, WaitSpec{nullptr, 0u, 0u}); });
+}
+
+template <int MODE>
+void spmv_mode(Emu *e, const double *vec, double *result) {
+  if (e->dyn) spmv_inst<MODE, true>(e, vec, result);
+  else spmv_inst<MODE, false>(e, vec, result);
+}
+}  // namespace
+
+extern "C" {
+
+int emu_tile_nnz(int dyn) { return dyn ? kTileNnzDyn : kTileNnz; }
+int emu_walk_uniform(void) { return ABFT_WALK_UNIFORM; }
+
+// create_matrix as abft_cuda_matrix_create_part does it: row pointers and check bits by the device kernels
+void *emu_create(int mode, const uint32_t *cols, const uint32_t *coo_rows, const double *vals, int N, int nnz) {
+  Emu *e = new Emu();
+  e->mode = mode;
+  e->n_rows = e->n_cols = (uint32_t)N;
+  e->nnz = (uint32_t)nnz;
+  const size_t nz = (size_t)std::max(nnz, 1);
+  e->cols.assign(nz + 16, 0u);
+  e->vals.assign(nz + 16, 0.0);
+  e->rowptr.assign((size_t)N + 1 + 16, 0u);
+  for (int i = 0; i < nnz; i++) { e->cols[i] = cols[i]; e->vals[i] = vals[i]; }
+  memset(&e->log, 0, sizeof e->log);
+  e->partials.assign(1 << 16, 0.0);
+  e->smem = (unsigned char *)aligned_alloc(128, (std::max(SpmvCfg<true>::dyn_smem, SpmvCfg<false>::dyn_smem) + 127) / 128 * 128);
+  fill_crc_tables();
+  emu::launch(2, kBlock, [&] { rowptr_kernel(coo_rows, (uint32_t)nnz, (uint32_t)N, 0u, e->rowptr.data()); });
+  if (mode >= ABFT_MODE_SED && mode <= ABFT_MODE_SECDED && nnz > 0)
+    emu::launch(2, kBlock, [&] { encode_elements_kernel(mode, e->cols.data(), e->vals.data(), (uint32_t)nnz); });
+  else if (mode == ABFT_MODE_CRC32C && N > 0)
+    emu::launch(2, kBlock, [&] { encode_crc_rows_kernel(e->rowptr.data(), e->cols.data(), e->vals.data(), (uint32_t)N); });
+  return e;
+}
+
+void emu_destroy(void *h) {
+  Emu *e = (Emu *)h;
+  free(e->smem);
+  delete e;
+}
+
+// the work decomposition (from abft_cuda_plan_tiles of the real library: host logic, no device needed)
+void emu_set_tiles(void *h, const uint32_t *recs, int n_tiles, int dyn, int grid) {
+  Emu *e = (Emu *)h;
+  e->tiles.resize((size_t)n_tiles);
+  for (int i = 0; i < n_tiles; i++) e->tiles[i] = Tile{recs[4 * i], recs[4 * i + 1], recs[4 * i + 2], recs[4 * i + 3]};
+  e->dyn = dyn != 0;
+  e->grid = grid;
+}
+
+uint32_t *emu_cols(void *h) { return ((Emu *)h)->cols.data(); }
+uint32_t *emu_rowptr(void *h) { return ((Emu *)h)->rowptr.data(); }
+double *emu_values(void *h) { return ((Emu *)h)->vals.data(); }
+
+void emu_flip(void *h, int index, int bit) {
+  Emu *e = (Emu *)h;
+  emu::launch(1, 32, [&] { flip_bit_kernel(e->cols.data(), e->vals.data(), (uint32_t)index, bit); });
+}
+
+// returns the number of raw (unsorted) log records copied to out[0..cap); *dot_out = the fused dot(vec, result)
+int emu_spmv(void *h, const double *vec, double *result, abft_event *out, int cap, double *dot_out) {
+  Emu *e = (Emu *)h;
+  e->log.count = 0;
+  e->flag = 0;
+  emu::g_dyn_smem = e->smem;
+  if (e->tiles.empty()) {
+    *dot_out = 0.0;
+    return 0;
+  }
+  switch (e->mode) {
+    case ABFT_MODE_NONE: spmv_mode<ABFT_MODE_NONE>(e, vec, result); break;
+    case ABFT_MODE_CONSTRAINTS: spmv_mode<ABFT_MODE_CONSTRAINTS>(e, vec, result); break;
+    case ABFT_MODE_SED: spmv_mode<ABFT_MODE_SED>(e, vec, result); break;
+    case ABFT_MODE_SEC7: spmv_mode<ABFT_MODE_SEC7>(e, vec, result); break;
+    case ABFT_MODE_SEC8: spmv_mode<ABFT_MODE_SEC8>(e, vec, result); break;
+    case ABFT_MODE_SECDED: spmv_mode<ABFT_MODE_SECDED>(e, vec, result); break;
+    case ABFT_MODE_CRC32C: spmv_mode<ABFT_MODE_CRC32C>(e, vec, result); break;
+    default: return -1;
+  }
+  *dot_out = e->scal_host;
+  if (e->scal_host != e->scal_dev && !(e->scal_host != e->scal_host)) return -2;  // device slot and host mirror differ
+  if (e->counter != 0 || e->tile_counter != 0) return -3;                         // not re-armed for the next launch
+  const int n = (int)std::min<unsigned>(e->log.count, (unsigned)std::min(cap, kLogCap));
+  for (int i = 0; i < n; i++) out[i] = e->log.ev[i];
+  return n;
+}
+
+// the vector kernels through the same machinery (host-scalar flavour)
+double emu_dot(void *h, const double *a, const double *b, int N, int grid) {
+  Emu *e = (Emu *)h;
+  const ReduceOut red = reduce_of(e);
+  emu::launch(grid, kBlock, [&] { dot_kernel(a, b, N, 1, red, nullptr); });
+  return e->scal_host;
+}
+double emu_calc_xr(void *h, double *x, double *r, const double *p, const double *w, double alpha, int N, int grid) {
+  Emu *e = (Emu *)h;
+  const ReduceOut red = reduce_of(e);
+  emu::launch(grid, kBlock, [&] { calc_xr_kernel<false>(x, r, p, w, ScalarArg{alpha, nullptr, nullptr}, N, 1, red, nullptr); });
+  return e->scal_host;
+}
+void emu_calc_p(double *p, const double *r, double beta, int N, int grid) {
+  emu::launch(grid, kBlock, [&] { calc_p_kernel<false>(p, r, ScalarArg{beta, nullptr, nullptr}, N, 1, nullptr); });
+}
+
+}  // extern "C"

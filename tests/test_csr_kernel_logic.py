@@ -1,0 +1,346 @@
+"""The LOGIC of the CSR kernels (abft-sparse-cg_b200/csrc/spmv.cuh, encode.cuh, vecops.cuh), executed on the CPU.
+
+There is no GPU in the build container, so the CPU suite checks the flagship kernels this way too: the product's own
+kernel source is compiled by g++ against a multi-threaded shim of the CUDA built-ins (tests/helpers/cuda_shim_mt/:
+a CTA runs as 256 real threads, __syncthreads and the warp collectives are barriers, the mbarrier / bulk-copy PTX
+helpers are a small state machine + memcpy) and compared with the oracle, which is pinned to the reference.  The work
+decomposition comes from the real library's abft_cuda_plan_tiles (host logic).  Same bars as tests/test_gpu_parity.py.
+What this cannot see: memory ordering on the device, TMA alignment rules, launch configuration, performance.
+
+The shipped configuration is run in full; the opt-in ABFT_WALK_UNIFORM variant on the tiles it changes.
+"""
+import ctypes as C
+import importlib.util
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"]
+FATAL = {1, 4, 5, 6, 7, 8, 9}          # every kind but CORRECTED_BIT (2) and CORRECTED_PARITY (3)
+ROW_EVENTS = {5, 6, 9}                 # ROW_SIZE, ROW_ORDER, CRC_ROW
+REGULAR = 1 << 16
+
+
+class Event(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("index", C.c_uint32), ("bit", C.c_uint32)]
+
+
+def _build(tmp, name, flags):
+    so = str(tmp / f"libcsr_emul_{name}.so")
+    h = os.path.join(ROOT, "tests", "helpers")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-pthread", *flags,
+                    "-I" + os.path.join(h, "cuda_shim_mt"), "-o", so, os.path.join(h, "csr_emul.cpp")], check=True)
+    L = C.CDLL(so)
+    u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+    f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    L.emu_create.restype = C.c_void_p
+    L.emu_create.argtypes = [C.c_int, u32p, u32p, f64p, C.c_int, C.c_int]
+    L.emu_destroy.argtypes = [C.c_void_p]
+    L.emu_set_tiles.argtypes = [C.c_void_p, u32p, C.c_int, C.c_int, C.c_int]
+    for f, t in ((L.emu_cols, C.c_uint32), (L.emu_rowptr, C.c_uint32), (L.emu_values, C.c_double)):
+        f.restype = C.POINTER(t)
+        f.argtypes = [C.c_void_p]
+    L.emu_flip.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.emu_spmv.restype = C.c_int
+    L.emu_spmv.argtypes = [C.c_void_p, f64p, f64p, C.POINTER(Event), C.c_int, C.POINTER(C.c_double)]
+    L.emu_dot.restype = C.c_double
+    L.emu_dot.argtypes = [C.c_void_p, f64p, f64p, C.c_int, C.c_int]
+    L.emu_calc_xr.restype = C.c_double
+    L.emu_calc_xr.argtypes = [C.c_void_p, f64p, f64p, f64p, f64p, C.c_double, C.c_int, C.c_int]
+    L.emu_calc_p.argtypes = [f64p, f64p, C.c_double, C.c_int, C.c_int]
+    return L
+
+
+@pytest.fixture(scope="module")
+def EMU(tmp_path_factory):
+    L = _build(tmp_path_factory.mktemp("csr_emu"), "shipped", [])
+    assert L.emu_walk_uniform() == 0
+    return L
+
+
+@pytest.fixture(scope="module")
+def EMU_UNIFORM(tmp_path_factory):
+    L = _build(tmp_path_factory.mktemp("csr_emu_u"), "walk_uniform", ["-DABFT_WALK_UNIFORM=1"])
+    assert L.emu_walk_uniform() == 1
+    return L
+
+
+class EmuMatrix:
+    """create_matrix + the tile plan, as abft_cuda_matrix_create_part does it."""
+
+    def __init__(self, L, pkg, mode, t, grid=3):
+        self.L, self.mode, self.N, self.nnz = L, mode, t.N, int(t.cols.shape[0])
+        self.h = L.emu_create(MODES.index(mode), np.ascontiguousarray(t.cols, dtype=np.uint32),
+                              np.ascontiguousarray(t.rows, dtype=np.uint32), np.ascontiguousarray(t.vals, dtype=np.float64),
+                              t.N, self.nnz)
+        assert self.h
+        lib = pkg.capi.load()
+        rowptr = self.rowptr.copy()
+
+        def plan(tile_nnz):
+            n = lib.abft_cuda_plan_tiles(rowptr.ctypes.data, t.N, tile_nnz, None, 0)
+            out = np.zeros((max(n, 1), 4), dtype=np.uint32)
+            assert lib.abft_cuda_plan_tiles(rowptr.ctypes.data, t.N, tile_nnz, out.ctypes.data, n) == n
+            return out[:n]
+        tiles = plan(L.emu_tile_nnz(0))
+        self.dyn = bool(np.any((tiles[:, 3] & REGULAR) == 0)) and mode != "crc32c" if len(tiles) else False
+        if self.dyn:
+            tiles = plan(L.emu_tile_nnz(1))
+        self.tiles = tiles
+        L.emu_set_tiles(self.h, np.ascontiguousarray(tiles.reshape(-1)) if len(tiles) else np.zeros(4, np.uint32),
+                        len(tiles), int(self.dyn), grid)
+
+    @property
+    def cols(self):
+        return np.ctypeslib.as_array(self.L.emu_cols(self.h), shape=(max(self.nnz, 1),))[:self.nnz]
+
+    @property
+    def rowptr(self):
+        return np.ctypeslib.as_array(self.L.emu_rowptr(self.h), shape=(self.N + 1,))
+
+    @property
+    def values(self):
+        return np.ctypeslib.as_array(self.L.emu_values(self.h), shape=(max(self.nnz, 1),))[:self.nnz]
+
+    def flip(self, index, bit):
+        self.L.emu_flip(self.h, index, bit)
+
+    def spmv(self, vec):
+        """-> (result, fatal, events, dot) with the events ordered and cut the way abft_cuda_poll_events does"""
+        out = np.full(self.N, np.nan)
+        log = (Event * 4096)()
+        dot = C.c_double(0.0)
+        n = self.L.emu_spmv(self.h, np.ascontiguousarray(vec, dtype=np.float64), out, log, 4096, C.byref(dot))
+        assert n >= 0, n
+        cons = self.mode == "constraints"
+
+        def key(e):
+            kind, index, bit = e
+            rowev = kind in ROW_EVENTS
+            return ((index if rowev else bit), (0 if rowev else 1), index, kind) if cons else (index, 0, bit, kind)
+        raw = sorted(((log[i].kind, log[i].index, log[i].bit) for i in range(n)), key=key)
+        events, fatal = [], False
+        for kind, index, bit in raw:
+            if cons and kind in (7, 8):
+                bit = 0                       # COL_* events carry their row in `bit` for ordering only
+            if events and events[-1] == (kind, index, bit):
+                continue
+            events.append((kind, index, bit))
+            if kind in FATAL:
+                fatal = True
+                break
+        return out, fatal, events, dot.value
+
+    def close(self):
+        self.L.emu_destroy(self.h)
+
+
+def shapes(mg):
+    rng = np.random.default_rng(11)
+
+    def ragged():
+        N = 700
+        lens = rng.integers(0, 10, N)
+        lens[[0, 5, 6, 300]] = 0
+        lens[-3:] = 0
+        rows = np.repeat(np.arange(N), lens)
+        cols = np.concatenate([np.sort(rng.choice(N, l, replace=False)) for l in lens if l > 0])
+        return mg.Triplets(cols, rows, rng.standard_normal(rows.shape[0]), N)
+
+    def short_rows():
+        N = 900
+        lens = rng.integers(1, 4, N)
+        rows = np.repeat(np.arange(N), lens)
+        cols = np.concatenate([np.sort(rng.choice(N, l, replace=False)) for l in lens])
+        return mg.Triplets(cols, rows, rng.standard_normal(rows.shape[0]), N)
+
+    def long_rows():
+        N = 6000
+        lens = np.full(N, 3)
+        lens[[10, 3000, 5999]] = [4000, 2049, 2500]
+        rows = np.repeat(np.arange(N), lens)
+        cols = np.concatenate([np.sort(rng.choice(N, l, replace=False)) for l in lens])
+        return mg.Triplets(cols, rows, rng.standard_normal(rows.shape[0]), N)
+
+    return {
+        "p2d_40": lambda: mg.poisson2d(40),                 # 5-point: walks of 5, several tiles per CTA
+        "p2d_12_b3": lambda: mg.poisson2d(12, 3),
+        "p3d_12": lambda: mg.poisson3d(12),                 # 7-point: walks of 7
+        "powerlaw": lambda: mg.powerlaw(3000, 60000, seed=2),                                   # dynamic schedule
+        "powerlaw_dense": lambda: mg.powerlaw(3000, 300000, alpha=1.6, max_deg=1200, seed=9),   # rows of 100s
+        "ragged": ragged,
+        "short_rows": short_rows,
+        "long_rows": long_rows,                             # rows longer than a tile
+        "one_by_one": lambda: mg.Triplets([0], [0], [2.5], 1),
+    }
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_create_matrix_and_clean_spmv(EMU, pkg, O, mode):
+    rng = np.random.default_rng(3)
+    for name, build in shapes(pkg.matgen).items():
+        t = build()
+        em = EmuMatrix(EMU, pkg, mode, t)
+        om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+        assert np.array_equal(em.rowptr, om.rows), name
+        assert np.array_equal(em.cols, om.cols), name
+        assert np.array_equal(em.values.view(np.uint64), om.values.view(np.uint64)), name
+        vec = rng.standard_normal(t.N)
+        y, fatal, events, dot = em.spmv(vec)
+        y0, fatal0, ev0 = om.spmv(vec)
+        assert not fatal and not fatal0 and events == [] and ev0 == [], (name, events)
+        lens = np.bincount(t.rows, minlength=t.N)
+        seq = lens <= 32          # sequential order kept: regular tiles, and rows of up to 32 elements anywhere
+        assert np.array_equal(y[seq].view(np.uint64), y0[seq].view(np.uint64)), name
+        scale = np.abs(t.vals).max() * np.abs(vec).max() * max(int(lens.max()), 1)
+        assert np.max(np.abs(y - y0)) <= 1e-13 * scale, name
+        exact = float(np.dot(vec, y0))
+        assert abs(dot - exact) <= 1e-10 * max(np.abs(vec * y0).sum(), 1e-300), name
+        # the schedule must not show: same bits with one CTA taking every tile
+        em1 = EmuMatrix(EMU, pkg, mode, t, grid=1)
+        y1, _, _, dot1 = em1.spmv(vec)
+        assert np.array_equal(y1.view(np.uint64), y.view(np.uint64)), name
+        if em.dyn:
+            assert np.float64(dot1).view(np.uint64) == np.float64(dot).view(np.uint64), name   # per-tile partials
+        em.close()
+        em1.close()
+
+
+@pytest.mark.parametrize("mode", ["sed", "sec7", "sec8", "secded", "crc32c"])
+@pytest.mark.parametrize("shape", ["p3d_12", "powerlaw", "long_rows"])
+def test_single_and_double_flips(EMU, pkg, O, mode, shape):
+    t = shapes(pkg.matgen)[shape]()
+    rng = np.random.default_rng(5)
+    vec = rng.standard_normal(t.N)
+    lens = np.bincount(t.rows, minlength=t.N)
+    scale = np.abs(t.vals).max() * np.abs(vec).max() * max(int(lens.max()), 1)
+    em = EmuMatrix(EMU, pkg, mode, t)
+    om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+    clean_c, clean_v = em.cols.copy(), em.values.copy()
+    for trial in range(8):
+        index = int(rng.integers(0, t.nnz))
+        bits = [int(b) for b in rng.choice(96, 1 + trial % 2, replace=False)]
+        for b in bits:
+            em.flip(index, b)
+            om.flip(index, b)
+        y, fatal, events, _ = em.spmv(vec)
+        y0, fatal0, ev0 = om.spmv(vec)
+        assert (fatal, events) == (fatal0, ev0), (shape, index, bits, events, ev0)
+        if not fatal:
+            assert np.array_equal(em.cols, om.cols) and np.array_equal(em.values.view(np.uint64), om.values.view(np.uint64))
+            assert np.max(np.abs(y - y0)) <= 1e-13 * scale or not np.all(np.isfinite(y0)), (shape, index, bits)
+        for arr, clean in ((em.cols, clean_c), (om.cols, clean_c), (em.values, clean_v), (om.values, clean_v)):
+            arr[index] = clean[index]
+    em.close()
+
+
+def test_constraints_violations(EMU, pkg, O):
+    """The four CONSTRAINTS checks, on regular and irregular tiles, incl. row pointers that leave the staged window."""
+    rng = np.random.default_rng(6)
+    for shape in ("p3d_12", "powerlaw", "long_rows"):
+        t = shapes(pkg.matgen)[shape]()
+        vec = rng.standard_normal(t.N)
+        rowptr = np.concatenate([[0], np.cumsum(np.bincount(t.rows, minlength=t.N))])
+        r = int(rng.integers(1, t.N - 2))
+        cases = [("col", int(rowptr[r]), 1 << 30), ("col", int(rowptr[r]) + 1, 0), ("col", int(rowptr[r + 1]) - 1, 0),
+                 ("row", r, t.nnz + 5), ("row", r + 1, int(rowptr[r]) - 1 if rowptr[r] > 0 else 0), ("row", r, 0),
+                 ("row", t.N, t.nnz + 1)]
+        if shape == "long_rows":
+            # rows longer than a tile are walked from the tile's own range: their row pointers must still be looked at
+            for lr in (10, 3000):
+                cases += [("row", lr + 1, t.nnz + 7), ("row", lr, int(rowptr[lr]) - 1), ("row", lr, int(rowptr[lr]) + 2),
+                          ("row", lr + 1, int(rowptr[lr + 1]) - 3), ("row", lr + 1, int(rowptr[lr]) - 1),
+                          ("col", int(rowptr[lr]) + 2100, 1 << 28), ("col", int(rowptr[lr]) + 17, 0)]
+        for what, where, value in cases:
+            em = EmuMatrix(EMU, pkg, "constraints", t)
+            om = O.OracleMatrix("constraints", t.cols, t.rows, t.vals, t.N)
+            if what == "col":
+                em.cols[where] = value
+                om.cols[where] = value
+            else:
+                em.rowptr[where] = value
+                om.rows[where] = value
+            y, fatal, events, _ = em.spmv(vec)
+            y0, fatal0, ev0 = om.spmv(vec)
+            assert (fatal, events) == (fatal0, ev0), (shape, what, where, value, events, ev0)
+            if not fatal:
+                lens = np.bincount(t.rows, minlength=t.N)
+                scale = np.abs(t.vals).max() * np.abs(vec).max() * int(lens.max())
+                assert np.max(np.abs(y - y0)) <= 1e-13 * scale, (shape, what, where, value)
+            em.close()
+
+
+@pytest.mark.parametrize("mode", ["none", "constraints", "sed", "sec7", "sec8", "secded"])
+def test_fuzz_distribution(EMU, pkg, O, mode):
+    """The differential-fuzz distribution of tools/fuzz_oracle_vs_ref.py (the oracle passes it against the live
+    reference): multi-bit, multi-element and row-pointer faults on small random matrices."""
+    spec = importlib.util.spec_from_file_location("fuzz_oracle_vs_ref", os.path.join(ROOT, "tools", "fuzz_oracle_vs_ref.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    rng = np.random.default_rng(77)
+    pool = fz.matrices(pkg.matgen, rng)
+    for trial in range(30):
+        t = pool[int(rng.integers(0, len(pool)))]
+        vec = rng.standard_normal(t.N)
+        flips, pokes = fz.draw_faults(rng, mode, t)
+        om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+        fz.corrupt_arrays(om.cols, om.rows, om.values, flips, pokes)
+        em = EmuMatrix(EMU, pkg, mode, t)
+        fz.corrupt_arrays(em.cols, em.rowptr, em.values, flips, pokes)
+        y0, fatal0, ev0 = om.spmv(vec)
+        y, fatal, events, _ = em.spmv(vec)
+        what = (mode, trial, flips, pokes)
+        assert (fatal, events) == (fatal0, ev0), (what, events, ev0)
+        if not fatal:
+            assert np.array_equal(em.cols, om.cols) and np.array_equal(em.values.view(np.uint64), om.values.view(np.uint64)), what
+            assert fz.same_result(y, y0, t, vec, om.cols, om.values, mode), what
+        em.close()
+
+
+@pytest.mark.parametrize("N", [1, 2, 7, 1000, 4099])
+def test_vector_kernels(EMU, pkg, O, N):
+    L = O.lib()
+    rng = np.random.default_rng(N)
+    x, r, p, w = (rng.standard_normal(N) for _ in range(4))
+    t = pkg.matgen.Triplets([0], [0], [1.0], 1)
+    em = EmuMatrix(EMU, pkg, "none", t)
+    grid = 3
+    assert abs(EMU.emu_dot(em.h, p, w, N, grid) - L.orc_dot(p, w, N)) <= 1e-12 * np.abs(p * w).sum()
+    x2, r2, p2 = x.copy(), r.copy(), p.copy()
+    xe, re_, pe = x.copy(), r.copy(), p.copy()
+    rr = EMU.emu_calc_xr(em.h, xe, re_, p, w, 0.37, N, grid)
+    rr0 = L.orc_calc_xr(x2, r2, p, w, 0.37, N)
+    assert np.array_equal(xe, x2) and np.array_equal(re_, r2) and abs(rr - rr0) <= 1e-12 * rr0
+    EMU.emu_calc_p(pe, re_, -1.25, N, grid)
+    L.orc_calc_p(p2, r2, -1.25, N)
+    assert np.array_equal(pe, p2)
+    em.close()
+
+
+@pytest.mark.parametrize("mode", ["none", "constraints", "sec7", "secded"])
+def test_walk_uniform_variant(EMU_UNIFORM, pkg, O, mode):
+    """-DABFT_WALK_UNIFORM=1 only changes the unrolled walk of regular tiles (rows of up to 7 elements): clean results
+    bit for bit on stencils (full warps take the unpredicated adds) and on ragged / short rows (mixed warps must not),
+    and the same events and repairs under faults."""
+    rng = np.random.default_rng(21)
+    for name in ("p3d_12", "p2d_40", "p2d_12_b3", "ragged", "short_rows", "one_by_one"):
+        t = shapes(pkg.matgen)[name]()
+        em = EmuMatrix(EMU_UNIFORM, pkg, mode, t)
+        om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+        vec = rng.standard_normal(t.N)
+        y, fatal, events, _ = em.spmv(vec)
+        y0, _, _ = om.spmv(vec)
+        assert not fatal and events == [] and np.array_equal(y.view(np.uint64), y0.view(np.uint64)), name
+        if mode in ("sec7", "secded") and t.nnz > 10:
+            for trial in range(4):
+                index, bit = int(rng.integers(0, t.nnz)), int(rng.integers(0, 96))
+                em.flip(index, bit)
+                om.flip(index, bit)
+                y, fatal, events, _ = em.spmv(vec)
+                y0, fatal0, ev0 = om.spmv(vec)
+                assert (fatal, events) == (fatal0, ev0), (name, index, bit)
+                assert np.array_equal(em.cols, om.cols) and np.array_equal(y.view(np.uint64), y0.view(np.uint64)), (name, index, bit)
+        em.close()

@@ -2,7 +2,8 @@
 arbitrary double values, 1..3 flips in each of 1..2 elements, row-pointer faults under `constraints`) through the C ABI
 on the device and through the CPU oracle -- which the CPU suite runs against the live reference on this very
 distribution (tests/test_oracle_ref.py).  Same events in the same order, same fatal verdict, same repaired matrix,
-same result[] bit for bit (the oracle and the kernels clamp out-of-range columns alike, so nothing is skipped here).
+same result[] (bit for bit where the kernels keep the sequential order: rows of up to 32 elements; the oracle and the
+kernels clamp out-of-range columns alike, so nothing is skipped here).
 
 Opt-in (ABFT_GPU_FUZZ=1) until it has been seen green on a B200: written in a session without GPU time left.
 """
@@ -55,7 +56,7 @@ def test_random_faults_gpu_equals_oracle(pkg, O, mode):
             cols, rows, vals = ctx.read_matrix(A)
             assert np.array_equal(cols, om.cols) and np.array_equal(vals.view(np.uint64), om.values.view(np.uint64)), what
             assert np.array_equal(rows, om.rows), what
-            assert np.array_equal(ctx.download(w).view(np.uint64), y0.view(np.uint64)), what
+            assert fz.same_result(ctx.download(w), y0, t, vec, om.cols, om.values, mode), what
         fatal_seen += fatal
         repaired_seen += bool(events) and not fatal
         for x in (v, w):

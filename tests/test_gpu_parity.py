@@ -240,7 +240,10 @@ def test_constraints_in_irregular_tiles(pkg, O):
         y0, fatal0, ev0 = om.spmv(vec)
         assert (fatal, events) == (fatal0, ev0) and fatal, (index, value)
         ctx.close()
-    for row, value in [(short, t.nnz + 5), (mid, 3), (mid + 1, int(rowptr[mid]) - 1)]:
+    # (the last two: the pointers of a row longer than a tile, which is walked from the tile's own range --
+    # found by running the kernel's logic on the CPU, tests/test_csr_kernel_logic.py)
+    for row, value in [(short, t.nnz + 5), (mid, 3), (mid + 1, int(rowptr[mid]) - 1),
+                       (longr + 1, t.nnz + 5), (longr + 1, int(rowptr[longr]) - 1)]:
         ctx, A, om = make(pkg, O, "constraints", t)
         ctx._ck(ctx.L.abft_cuda_matrix_poke_rowptr(ctx.ctx, A.handle, row, value), "poke")
         om.rows[row] = value
