@@ -114,6 +114,12 @@ static int ensure_tables(int device) {
   for (int s = 0; s < 4; s++)
     for (uint32_t i = 0; i < 256; i++) tab[s * 256 + i] = crc32c_table_entry(i, s);
   CK(cudaMemcpyToSymbol(g_crc_tab, tab.data(), sizeof(uint32_t) * 1024));
+#if ABFT_CRC_CHUNK
+  std::vector<uint32_t> chunk_tab((size_t)kCrcEntries);
+  for (int j = 0; j < kCrcChunks; j++)
+    for (uint32_t cc = 0; cc < (1u << crc_chunk_bits(j)); cc++) chunk_tab[(size_t)crc_chunk_base(j) + cc] = crc_chunk_entry(j, cc);
+  CK(cudaMemcpyToSymbol(g_crc_chunk_tab, chunk_tab.data(), sizeof(uint32_t) * (size_t)kCrcEntries));
+#endif
   if (device >= 0 && device < 64) g_tables_ready[device] = true;
   return 0;
 }

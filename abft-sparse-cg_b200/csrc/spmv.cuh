@@ -365,6 +365,62 @@ __device__ __forceinline__ uint32_t crc_word(uint32_t crc, uint32_t w, const uin
 
 __device__ uint32_t g_crc_tab[1024];  // filled by the host at library init
 
+// ---- experiment (opt-in, -DABFT_CRC_CHUNK=5 or 6): bank-conflict-free CRC tables for the spmv check.
+// The byte tables above are hit by 32 lanes at random: ~3.2-way bank conflicts, 41 shared-memory wavefronts per 32
+// elements, and the kernel is bound by exactly that.  The update of the state by one 32-bit word is linear in
+// x = crc ^ word, so x can be cut into chunks of any width B: crc' = xor_j T_j[chunk_j(x)], T_j[c] = F(c << jB) with F =
+// "advance the state over four zero bytes".  With B = 5 (6) the tables have 196 (324) entries in all, small enough to
+// give EVERY LANE ITS OWN COPY IN ITS OWN BANK -- entry e of lane l lives at word e*32 + l -- in 24.5 (40.5) KB of
+// static shared memory: 21 (18) conflict-free lookups per element instead of 12 conflicted ones, 24 (21) wavefronts
+// per 32 elements.  Logic checked on the CPU (tests/test_csr_kernel_logic.py); to be timed in round 2.
+#ifndef ABFT_CRC_CHUNK
+#define ABFT_CRC_CHUNK 0
+#endif
+#if ABFT_CRC_CHUNK
+constexpr int kCrcB = ABFT_CRC_CHUNK;
+constexpr int kCrcChunks = (32 + kCrcB - 1) / kCrcB;
+__host__ __device__ constexpr int crc_chunk_bits(int j) { return (32 - j * kCrcB) < kCrcB ? (32 - j * kCrcB) : kCrcB; }
+__host__ __device__ constexpr int crc_chunk_base(int j) {
+  int b = 0;
+  for (int k = 0; k < j; k++) b += 1 << crc_chunk_bits(k);
+  return b;
+}
+constexpr int kCrcEntries = crc_chunk_base(kCrcChunks);
+constexpr int kCrcSmemWords = kCrcEntries * 32;
+static_assert(kCrcSmemWords * 4 <= 44 * 1024, "chunk tables must fit the static shared-memory budget");
+// T_j[c]: the state four zero bytes after c << jB
+constexpr uint32_t crc_chunk_entry(int j, uint32_t c) {
+  uint32_t x = c << (j * kCrcB);
+  for (int k = 0; k < 4; k++) x = (x >> 8) ^ crc32c_table_entry(x & 0xFFu, 0);
+  return x;
+}
+__device__ uint32_t g_crc_chunk_tab[kCrcEntries];  // filled by the host at library init
+
+// tab_lane = the CTA's table + this thread's lane
+__device__ __forceinline__ uint32_t crc_word_chunked(uint32_t crc, uint32_t w, const uint32_t *tab_lane) {
+  const uint32_t x = crc ^ w;
+  uint32_t r = 0;
+#pragma unroll
+  for (int j = 0; j < kCrcChunks; j++) {
+    const uint32_t c = (x >> (j * kCrcB)) & ((1u << crc_chunk_bits(j)) - 1u);
+    r ^= tab_lane[(crc_chunk_base(j) + c) << 5];
+  }
+  return r;
+}
+constexpr int kCrcSpmvWords = kCrcSmemWords;
+#else
+constexpr int kCrcSpmvWords = 1024;
+#endif
+
+// one step of the spmv's row CRC with whichever tables this build uses (`tab`: see the kernel)
+__device__ __forceinline__ uint32_t crc_step(uint32_t crc, uint32_t w, const uint32_t *tab) {
+#if ABFT_CRC_CHUNK
+  return crc_word_chunked(crc, w, tab);
+#else
+  return crc_word(crc, w, tab);
+#endif
+}
+
 // multi-GPU: the peers whose pushes into vec[] must have landed before it is read
 struct WaitSpec {
   const CommWindow *me;  // local window
@@ -396,7 +452,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   __shared__ Tile s_tile[kStages];
   __shared__ uint32_t s_tidx[kStages];              // index of the staged tile (dynamic schedule: its partial's slot)
   __shared__ double s_wdot[2][kBlock / 32];         // dynamic schedule: the warps' dot() partials of a tile
-  __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? 1024 : 1];
+  __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? kCrcSpmvWords : 1];
   __shared__ double s_warp[kBlock / 32];
 
   if (active && *active == 0) return;  // device-resident loop already converged
@@ -432,7 +488,12 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   __syncthreads();
   if (tid == 0) fence_proxy_async();
   if (MODE == ABFT_MODE_CRC32C)
+#if ABFT_CRC_CHUNK
+    for (int i = tid; i < kCrcSmemWords; i += kBlock) s_crc[i] = g_crc_chunk_tab[i >> 5];  // one copy per lane / bank
+#else
     for (int i = tid; i < 1024; i += kBlock) s_crc[i] = g_crc_tab[i];
+#endif
+  const uint32_t *const crc_tab = s_crc + ((ABFT_CRC_CHUNK && MODE == ABFT_MODE_CRC32C) ? (threadIdx.x & 31) : 0);
   __syncthreads();
 
   const uint64_t stream_policy = l2_evict_first_policy();
@@ -576,9 +637,9 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           uint32_t w0, w1;
           split_value(A.values[i], w0, w1);
           if (e < 4) stored |= (cw >> 24) << (8 * e);
-          crc = crc_word(crc, w0, s_crc);
-          crc = crc_word(crc, w1, s_crc);
-          crc = crc_word(crc, cw & 0x00FFFFFFu, s_crc);
+          crc = crc_step(crc, w0, crc_tab);
+          crc = crc_step(crc, w1, crc_tab);
+          crc = crc_step(crc, cw & 0x00FFFFFFu, crc_tab);
         }
         if ((crc ^ 0xFFFFFFFFu) != stored) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + t.row_begin, 0);
       }
@@ -772,9 +833,9 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
               split_value(val, w0, w1);
               if (len >= 4) {
                 if (i - rs < 4) stored |= (cw >> 24) << (8 * (i - rs));
-                crc = crc_word(crc, w0, s_crc);
-                crc = crc_word(crc, w1, s_crc);
-                crc = crc_word(crc, cw & 0x00FFFFFFu, s_crc);
+                crc = crc_step(crc, w0, crc_tab);
+                crc = crc_step(crc, w1, crc_tab);
+                crc = crc_step(crc, cw & 0x00FFFFFFu, crc_tab);
               } else {
                 // too short to hold 32 CRC bits: SECDED check byte per element, detect-only
                 if ((overall_parity(w0, w1, cw) | syndrome7_any(w0, w1, cw)) & 1u) bad = true;

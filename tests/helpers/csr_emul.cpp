@@ -41,6 +41,10 @@ ReduceOut reduce_of(Emu *e) {
 void fill_crc_tables() {
   for (int s = 0; s < 4; s++)
     for (uint32_t i = 0; i < 256; i++) g_crc_tab[s * 256 + i] = crc32c_table_entry(i, s);
+#if ABFT_CRC_CHUNK
+  for (int j = 0; j < kCrcChunks; j++)
+    for (uint32_t c = 0; c < (1u << crc_chunk_bits(j)); c++) g_crc_chunk_tab[crc_chunk_base(j) + c] = crc_chunk_entry(j, c);
+#endif
 }
 
 template <int MODE, bool DYN>
@@ -74,6 +78,7 @@ extern "C" {
 
 int emu_tile_nnz(int dyn) { return dyn ? kTileNnzDyn : kTileNnz; }
 int emu_walk_uniform(void) { return ABFT_WALK_UNIFORM; }
+int emu_crc_chunk(void) { return ABFT_CRC_CHUNK; }
 
 // create_matrix as abft_cuda_matrix_create_part does it: row pointers and check bits by the device kernels
 void *emu_create(int mode, const uint32_t *cols, const uint32_t *coo_rows, const double *vals, int N, int nnz) {

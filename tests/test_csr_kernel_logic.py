@@ -31,7 +31,9 @@ class Event(C.Structure):
 def _build(tmp, name, flags):
     so = str(tmp / f"libcsr_emul_{name}.so")
     h = os.path.join(ROOT, "tests", "helpers")
-    subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-pthread", *flags,
+    # -fno-gnu-unique: the kernels' "shared memory" is function-local statics of templates; as GNU-unique symbols they
+    # would be merged across the differently configured builds loaded into this one process
+    subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-fno-gnu-unique", "-w", "-pthread", *flags,
                     "-I" + os.path.join(h, "cuda_shim_mt"), "-o", so, os.path.join(h, "csr_emul.cpp")], check=True)
     L = C.CDLL(so)
     u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
@@ -343,4 +345,37 @@ def test_walk_uniform_variant(EMU_UNIFORM, pkg, O, mode):
                 y0, fatal0, ev0 = om.spmv(vec)
                 assert (fatal, events) == (fatal0, ev0), (name, index, bit)
                 assert np.array_equal(em.cols, om.cols) and np.array_equal(y.view(np.uint64), y0.view(np.uint64)), (name, index, bit)
+        em.close()
+
+
+@pytest.mark.parametrize("chunk", [5, 6])
+def test_crc_chunk_table_variant(tmp_path_factory, pkg, O, chunk):
+    """-DABFT_CRC_CHUNK=5|6 (per-lane, bank-conflict-free CRC tables in the spmv check): the same verdicts as the byte
+    tables -- clean matrices pass (rows of >= 4 elements carry the CRC, shorter ones the SECDED byte), every single
+    and double flip in a CRC-protected row is caught, in regular tiles and in rows longer than a tile."""
+    L = _build(tmp_path_factory.mktemp(f"csr_emu_crc{chunk}"), f"crc{chunk}", [f"-DABFT_CRC_CHUNK={chunk}"])
+    assert L.emu_crc_chunk() == chunk
+    rng = np.random.default_rng(31 + chunk)
+    for name in ("p3d_12", "p2d_40", "ragged", "short_rows", "long_rows", "powerlaw"):
+        t = shapes(pkg.matgen)[name]()
+        em = EmuMatrix(L, pkg, "crc32c", t)
+        om = O.OracleMatrix("crc32c", t.cols, t.rows, t.vals, t.N)
+        assert np.array_equal(em.cols, om.cols), name            # (encode uses the byte tables in every build)
+        vec = rng.standard_normal(t.N)
+        y, fatal, events, _ = em.spmv(vec)
+        y0, _, _ = om.spmv(vec)
+        lens = np.bincount(t.rows, minlength=t.N)
+        scale = np.abs(t.vals).max() * np.abs(vec).max() * int(lens.max())
+        assert not fatal and events == [] and np.max(np.abs(y - y0)) <= 1e-13 * scale, (name, events)
+        clean_c, clean_v = em.cols.copy(), em.values.copy()
+        for trial in range(6):
+            index = int(rng.integers(0, t.nnz))
+            for b in rng.choice(96, 1 + trial % 2, replace=False):
+                em.flip(index, int(b))
+                om.flip(index, int(b))
+            _, fatal, events, _ = em.spmv(vec)
+            _, fatal0, ev0 = om.spmv(vec)
+            assert (fatal, events) == (fatal0, ev0), (name, index, events, ev0)
+            for arr, clean in ((em.cols, clean_c), (om.cols, clean_c), (em.values, clean_v), (om.values, clean_v)):
+                arr[index] = clean[index]
         em.close()
