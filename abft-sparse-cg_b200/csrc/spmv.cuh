@@ -396,14 +396,17 @@ constexpr uint32_t crc_chunk_entry(int j, uint32_t c) {
 }
 __device__ uint32_t g_crc_chunk_tab[kCrcEntries];  // filled by the host at library init
 
-// tab_lane = the CTA's table + this thread's lane
-__device__ __forceinline__ uint32_t crc_word_chunked(uint32_t crc, uint32_t w, const uint32_t *tab_lane) {
+// tab = the CTA's table, lane4 = 4 * lane: entry e of this lane is the word at byte offset e*128 + lane4.  Written so
+// that a lookup is shift, and-or (chunk and lane into one offset), load with the table's base as the immediate.
+__device__ __forceinline__ uint32_t crc_word_chunked(uint32_t crc, uint32_t w, const uint32_t *tab, uint32_t lane4) {
   const uint32_t x = crc ^ w;
   uint32_t r = 0;
 #pragma unroll
   for (int j = 0; j < kCrcChunks; j++) {
-    const uint32_t c = (x >> (j * kCrcB)) & ((1u << crc_chunk_bits(j)) - 1u);
-    r ^= tab_lane[(crc_chunk_base(j) + c) << 5];
+    const int s = j * kCrcB - 7;  // chunk j, times 128, = x shifted by this much and masked
+    const uint32_t shifted = s >= 0 ? (x >> (s >= 0 ? s : 0)) : (x << (s < 0 ? -s : 0));
+    const uint32_t off = (shifted & (((1u << crc_chunk_bits(j)) - 1u) << 7)) | lane4;
+    r ^= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab + crc_chunk_base(j) * 32) + off);
   }
   return r;
 }
@@ -413,12 +416,50 @@ constexpr int kCrcSpmvWords = 1024;
 #endif
 
 // one step of the spmv's row CRC with whichever tables this build uses (`tab`: see the kernel)
-__device__ __forceinline__ uint32_t crc_step(uint32_t crc, uint32_t w, const uint32_t *tab) {
+__device__ __forceinline__ uint32_t crc_step(uint32_t crc, uint32_t w, const uint32_t *tab, uint32_t lane4) {
 #if ABFT_CRC_CHUNK
-  return crc_word_chunked(crc, w, tab);
+  return crc_word_chunked(crc, w, tab, lane4);
 #else
   return crc_word(crc, w, tab);
 #endif
+}
+
+// ---- experiment (opt-in, -DABFT_CRC_WALK=1): an unrolled CRC32C row walk for regular tiles.
+// The shipped CRC path is the generic one-element-at-a-time loop (~110 instructions per element, next to 12 table
+// lookups with ~3-way bank conflicts); this is walk_chunk's shape for the CRC mode: all shared-memory loads, then
+// the serial CRC chain with the gathers in flight beside it, then the products in element order.  For rows of
+// 4..LEN elements (the CRC sits in the top bytes of the first four column words); anything else takes the loop.
+#ifndef ABFT_CRC_WALK
+#define ABFT_CRC_WALK 0
+#endif
+template <int LEN>
+__device__ __forceinline__ double walk_crc(uint32_t count, const uint32_t *s_cols, const double *s_vals, uint32_t n_cols,
+                                           const double *__restrict__ x, const uint32_t *crc_tab, uint32_t lane4, bool &bad) {
+  uint32_t c[LEN];
+  double v[LEN], xv[LEN];
+#pragma unroll
+  for (int k = 0; k < LEN; k++) {
+    c[k] = s_cols[k];
+    v[k] = s_vals[k];
+  }
+  uint32_t crc = 0xFFFFFFFFu, stored = 0;
+#pragma unroll
+  for (int k = 0; k < LEN; k++) {
+    const uint32_t col = c[k] & 0x00FFFFFFu;
+    xv[k] = __ldg(x + min(col, n_cols - 1u));
+    if (k < 4) stored |= (c[k] >> 24) << (8 * k);  // (count >= 4: these four are the row's own)
+    uint32_t w0, w1;
+    split_value(v[k], w0, w1);
+    uint32_t next = crc_step(crc, w0, crc_tab, lane4);
+    next = crc_step(next, w1, crc_tab, lane4);
+    next = crc_step(next, col, crc_tab, lane4);
+    crc = ((uint32_t)k < count) ? next : crc;        // slots past the row's end hold the next row's elements
+  }
+  bad = (crc ^ 0xFFFFFFFFu) != stored;
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < LEN; k++) sum = add_if(sum, __dmul_rn(v[k], xv[k]), (uint32_t)k < count);
+  return sum;
 }
 
 // multi-GPU: the peers whose pushes into vec[] must have landed before it is read
@@ -493,7 +534,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
 #else
     for (int i = tid; i < 1024; i += kBlock) s_crc[i] = g_crc_tab[i];
 #endif
-  const uint32_t *const crc_tab = s_crc + ((ABFT_CRC_CHUNK && MODE == ABFT_MODE_CRC32C) ? (threadIdx.x & 31) : 0);
+  const uint32_t crc_lane4 = (threadIdx.x & 31u) * 4u;  // (chunked tables: this lane's copy)
   __syncthreads();
 
   const uint64_t stream_policy = l2_evict_first_policy();
@@ -637,9 +678,9 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           uint32_t w0, w1;
           split_value(A.values[i], w0, w1);
           if (e < 4) stored |= (cw >> 24) << (8 * e);
-          crc = crc_step(crc, w0, crc_tab);
-          crc = crc_step(crc, w1, crc_tab);
-          crc = crc_step(crc, cw & 0x00FFFFFFu, crc_tab);
+          crc = crc_step(crc, w0, s_crc, crc_lane4);
+          crc = crc_step(crc, w1, s_crc, crc_lane4);
+          crc = crc_step(crc, cw & 0x00FFFFFFu, s_crc, crc_lane4);
         }
         if ((crc ^ 0xFFFFFFFFu) != stored) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + t.row_begin, 0);
       }
@@ -818,6 +859,23 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
               sum = walk_chunk<MODE, 4>(sum, base, len - base, sc, sv, A.n_cols, x, suspect);
           careful = (suspect & 1u) != 0;  // a check tripped somewhere in this row: walk it again, carefully
         }
+#if ABFT_CRC_WALK
+        if (MODE == ABFT_MODE_CRC32C) {
+          const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the CTA
+          const uint32_t len = re - rs;
+          if (max_len <= 7 && len >= 4) {
+            const uint32_t *sc = B.cols + (rs - cb);
+            const double *sv = B.vals + (rs - vb);
+            bool bad = false;
+            if (max_len <= 4) sum = walk_crc<4>(len, sc, sv, A.n_cols, x, s_crc, crc_lane4, bad);
+            else if (max_len == 5) sum = walk_crc<5>(len, sc, sv, A.n_cols, x, s_crc, crc_lane4, bad);
+            else if (max_len == 6) sum = walk_crc<6>(len, sc, sv, A.n_cols, x, s_crc, crc_lane4, bad);
+            else sum = walk_crc<7>(len, sc, sv, A.n_cols, x, s_crc, crc_lane4, bad);
+            if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
+            careful = false;
+          }
+        }
+#endif
         if (careful) {
           sum = 0.0;
           if (MODE == ABFT_MODE_CONSTRAINTS) {
@@ -833,9 +891,9 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
               split_value(val, w0, w1);
               if (len >= 4) {
                 if (i - rs < 4) stored |= (cw >> 24) << (8 * (i - rs));
-                crc = crc_step(crc, w0, crc_tab);
-                crc = crc_step(crc, w1, crc_tab);
-                crc = crc_step(crc, cw & 0x00FFFFFFu, crc_tab);
+                crc = crc_step(crc, w0, s_crc, crc_lane4);
+                crc = crc_step(crc, w1, s_crc, crc_lane4);
+                crc = crc_step(crc, cw & 0x00FFFFFFu, s_crc, crc_lane4);
               } else {
                 // too short to hold 32 CRC bits: SECDED check byte per element, detect-only
                 if ((overall_parity(w0, w1, cw) | syndrome7_any(w0, w1, cw)) & 1u) bad = true;

@@ -348,13 +348,14 @@ def test_walk_uniform_variant(EMU_UNIFORM, pkg, O, mode):
         em.close()
 
 
-@pytest.mark.parametrize("chunk", [5, 6])
-def test_crc_chunk_table_variant(tmp_path_factory, pkg, O, chunk):
-    """-DABFT_CRC_CHUNK=5|6 (per-lane, bank-conflict-free CRC tables in the spmv check): the same verdicts as the byte
-    tables -- clean matrices pass (rows of >= 4 elements carry the CRC, shorter ones the SECDED byte), every single
+@pytest.mark.parametrize("chunk,walk", [(5, 0), (6, 0), (0, 1), (6, 1)])
+def test_crc_chunk_table_variant(tmp_path_factory, pkg, O, chunk, walk):
+    """-DABFT_CRC_CHUNK=5|6 (per-lane, bank-conflict-free CRC tables in the spmv check) and -DABFT_CRC_WALK=1 (the unrolled
+    CRC row walk of regular tiles): the same verdicts as the shipped loop over byte tables -- clean matrices pass (rows of >= 4 elements carry the CRC, shorter ones the SECDED byte), every single
     and double flip in a CRC-protected row is caught, in regular tiles and in rows longer than a tile."""
-    L = _build(tmp_path_factory.mktemp(f"csr_emu_crc{chunk}"), f"crc{chunk}", [f"-DABFT_CRC_CHUNK={chunk}"])
-    assert L.emu_crc_chunk() == chunk
+    L = _build(tmp_path_factory.mktemp(f"csr_emu_crc{chunk}{walk}"), f"crc{chunk}{walk}",
+               [f"-DABFT_CRC_CHUNK={chunk}", f"-DABFT_CRC_WALK={walk}"])
+    assert L.emu_crc_chunk() == chunk and L.emu_crc_walk() == walk
     rng = np.random.default_rng(31 + chunk)
     for name in ("p3d_12", "p2d_40", "ragged", "short_rows", "long_rows", "powerlaw"):
         t = shapes(pkg.matgen)[name]()
@@ -367,6 +368,7 @@ def test_crc_chunk_table_variant(tmp_path_factory, pkg, O, chunk):
         lens = np.bincount(t.rows, minlength=t.N)
         scale = np.abs(t.vals).max() * np.abs(vec).max() * int(lens.max())
         assert not fatal and events == [] and np.max(np.abs(y - y0)) <= 1e-13 * scale, (name, events)
+        assert np.array_equal(y[lens <= 32].view(np.uint64), y0[lens <= 32].view(np.uint64)), name
         clean_c, clean_v = em.cols.copy(), em.values.copy()
         for trial in range(6):
             index = int(rng.integers(0, t.nnz))

@@ -5,7 +5,7 @@
 #   tools/ab_variants.sh run [reps]       # on the GPU box: parity tests + spmv timings per variant -> gpurun_out/ab_variants.jsonl
 #
 # Variants (name:flags).  `base` is the shipped configuration.  Knobs: spmv.cuh (ABFT_WALK_UNIFORM, ABFT_TILE_STATIC,
-# ABFT_TILE_DYN, ABFT_SPMV_MINB, ABFT_ELEM_BATCH, ABFT_CRC_CHUNK).  A variant is only ever adopted after `run` shows it parity-green
+# ABFT_TILE_DYN, ABFT_SPMV_MINB, ABFT_ELEM_BATCH, ABFT_CRC_CHUNK, ABFT_CRC_WALK).  A variant is only ever adopted after `run` shows it parity-green
 # and faster; numbers taken here are kernel timings (CUDA events), not bench values.
 set -euo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
@@ -19,6 +19,9 @@ VARIANTS=(
   "crc5:-DABFT_CRC_CHUNK=5"
   "crc5_t1536:-DABFT_CRC_CHUNK=5 -DABFT_TILE_STATIC=1536"
   "crc6:-DABFT_CRC_CHUNK=6"
+  "crcwalk:-DABFT_CRC_WALK=1"
+  "crcwalk6:-DABFT_CRC_WALK=1 -DABFT_CRC_CHUNK=6"
+  "crcwalk5_t1536:-DABFT_CRC_WALK=1 -DABFT_CRC_CHUNK=5 -DABFT_TILE_STATIC=1536"
 )
 case "${1:-}" in
   build)
