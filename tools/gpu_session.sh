@@ -1,0 +1,37 @@
+#!/usr/bin/env bash
+# What the next session with GPU minutes should run first (one `gpurun --timeout 1500 -- tools/gpu_session.sh` call, 1 GPU):
+# everything that was written without a GPU gets seen on hardware, then the A/B kit picks kernel variants.
+# Each stage writes under gpurun_out/ and never aborts the following ones.
+#   1 tests    pytest -m gpu, plus the opt-in suites (GPU fuzz, cg-coo-cuda CLI)
+#   2 ab       tools/ab_variants.sh run  (parity per variant, then spmv timings: none / sec7 / secded / crc32c on 256^3)
+#   3 coo      COO spmv timings (tools/time_spmv.py --format coo)
+#   4 c5       bench.py --workload powerlaw at the size BASELINE names (N = 2^23, ~1.9e8 non-zeros), sec7 and constraints
+#   5 bench    the default bench line
+# Usage: tools/gpu_session.sh [stage ...]   (default: all)
+set -uo pipefail
+ROOT="$(cd "$(dirname "$0")/.." && pwd)"
+cd "$ROOT"
+mkdir -p gpurun_out
+stages=("$@"); [ ${#stages[@]} -eq 0 ] && stages=(tests ab coo c5 bench)
+for st in "${stages[@]}"; do
+  case "$st" in
+    tests)
+      python -m pytest tests -q -m gpu > gpurun_out/session_pytest_gpu.txt 2>&1; echo "pytest -m gpu: rc=$?"
+      ABFT_GPU_FUZZ=1 ABFT_COO_CLI_TESTS=1 python -m pytest tests/test_gpu_fuzz.py tests/test_gpu_cli_coo.py -q -m gpu \
+          > gpurun_out/session_pytest_optin.txt 2>&1; echo "opt-in suites: rc=$?"
+      tail -3 gpurun_out/session_pytest_gpu.txt gpurun_out/session_pytest_optin.txt ;;
+    ab)
+      tools/ab_variants.sh run 50 > gpurun_out/session_ab.txt 2>&1; echo "ab kit: rc=$?"; tail -40 gpurun_out/session_ab.txt ;;
+    coo)
+      python tools/time_spmv.py --workload poisson3d --format coo --modes none,sed,sec7,secded --reps 30 --warm 50 \
+          > gpurun_out/session_coo.jsonl 2> gpurun_out/session_coo.err; echo "coo timings: rc=$?"; cat gpurun_out/session_coo.jsonl ;;
+    c5)
+      for m in sec7 constraints; do
+        python bench.py --workload powerlaw --mode $m --steps 100 --warmup 10 --all-modes 0 \
+            > gpurun_out/session_c5_$m.json 2> gpurun_out/session_c5_$m.err; echo "C5 $m: rc=$?"; cat gpurun_out/session_c5_$m.json
+      done ;;
+    bench)
+      python bench.py > gpurun_out/session_bench.json 2> gpurun_out/session_bench.err; echo "bench: rc=$?"; cat gpurun_out/session_bench.json ;;
+    *) echo "unknown stage $st" ;;
+  esac
+done
