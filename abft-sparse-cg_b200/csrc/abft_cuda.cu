@@ -1274,14 +1274,21 @@ int abft_cuda_dist_cg_solve(abft_ctx *c, abft_comm *m, abft_matrix *A, const abf
 struct abft_coo_matrix {
   CooView view{};
   uint32_t *d_perm = nullptr, *d_colptr = nullptr;
+  uint32_t *d_pos = nullptr;     // grouped layout (ABFT_CUDA_COO_LAYOUT=grouped): element index -> slot; else null
+  std::vector<uint32_t> h_perm;  // grouped layout: host copy, to hand the elements back in the caller's order
 };
 
 template <int MODE>
 static void launch_coo_spmv_mode(abft_ctx *c, const abft_coo_matrix *m, const double *vec, double *result) {
   LogRef L{c->d_log, c->h_flag};
   const int grid = std::max(1, std::min((int)((m->view.N + kBlock - 1) / kBlock), c->num_sms * 8));
-  coo_spmv_kernel<MODE><<<grid, kBlock, 0, c->stream>>>(m->view, vec, result, L);
-  coo_stray_kernel<MODE><<<1, 32, 0, c->stream>>>(m->view, vec, result);
+  if (m->view.pos) {
+    coo_spmv_kernel<MODE, true><<<grid, kBlock, 0, c->stream>>>(m->view, vec, result, L);
+    coo_stray_kernel<MODE, true><<<1, 32, 0, c->stream>>>(m->view, vec, result);
+  } else {
+    coo_spmv_kernel<MODE, false><<<grid, kBlock, 0, c->stream>>>(m->view, vec, result, L);
+    coo_stray_kernel<MODE, false><<<1, 32, 0, c->stream>>>(m->view, vec, result);
+  }
 }
 
 extern "C" {
@@ -1335,9 +1342,20 @@ abft_coo_matrix *abft_cuda_coo_matrix_create(abft_ctx *c, const uint32_t *column
       cudaFree(m->view.stray);
       cudaFree(m->d_perm);
       cudaFree(m->d_colptr);
+      cudaFree(m->d_pos);
       delete m;
     }
   } cleanup{m, d_cols, d_rows, d_vals};
+  // opt-in: store the elements in group order (coo.cuh, GROUPED) -- not yet run or timed on a GPU
+  const char *layout = getenv("ABFT_CUDA_COO_LAYOUT");
+  const bool grouped = layout && !strcmp(layout, "grouped") && nnz > 0;
+  std::vector<uint32_t> pos;
+  if (grouped) {
+    pos.resize((size_t)nnz);
+    for (int k = 0; k < nnz; k++) pos[perm[(size_t)k]] = (uint32_t)k;
+    CKP(cudaMalloc(&m->d_pos, sizeof(uint32_t) * nz));
+    CKP(cudaMemcpyAsync(m->d_pos, pos.data(), sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+  }
   CKP(cudaMalloc(&m->view.elements, sizeof(uint4) * nz));
   CKP(cudaMalloc(&m->view.stray, sizeof(uint32_t) * (1 + kMaxStray)));
   CKP(cudaMalloc(&m->d_perm, sizeof(uint32_t) * nz));
@@ -1353,7 +1371,7 @@ abft_coo_matrix *abft_cuda_coo_matrix_create(abft_ctx *c, const uint32_t *column
     CKP(cudaMemcpyAsync(d_rows, rows, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
     CKP(cudaMemcpyAsync(d_vals, values, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
     coo_encode_kernel<<<c->num_sms * 8, kBlock, 0, c->stream>>>(c->mode, d_cols, d_rows, d_vals, m->view.elements,
-                                                                 (uint32_t)nnz);
+                                                                 (uint32_t)nnz, m->d_pos);
     c->launches++;
     CKP(cudaGetLastError());
   }
@@ -1362,6 +1380,8 @@ abft_coo_matrix *abft_cuda_coo_matrix_create(abft_ctx *c, const uint32_t *column
   m->view.colptr = m->d_colptr;
   m->view.N = (uint32_t)N;
   m->view.nnz = (uint32_t)nnz;
+  m->view.pos = m->d_pos;
+  if (grouped) m->h_perm.swap(perm);
   cleanup.armed = false;
   return m;
 }
@@ -1376,6 +1396,7 @@ void abft_cuda_coo_matrix_destroy(abft_ctx *c, abft_coo_matrix *m) {
   cudaFree(m->view.stray);
   cudaFree(m->d_perm);
   cudaFree(m->d_colptr);
+  cudaFree(m->d_pos);
   delete m;
 }
 
@@ -1385,7 +1406,15 @@ int abft_cuda_coo_matrix_read(abft_ctx *c, const abft_coo_matrix *m, void *eleme
   REQUIRE(c && m && elements_out, "null argument");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
-  if (m->view.nnz) CK(cudaMemcpy(elements_out, m->view.elements, sizeof(uint4) * m->view.nnz, cudaMemcpyDeviceToHost));
+  if (m->view.nnz && !m->view.pos)
+    CK(cudaMemcpy(elements_out, m->view.elements, sizeof(uint4) * m->view.nnz, cudaMemcpyDeviceToHost));
+  if (m->view.nnz && m->view.pos) {
+    // grouped layout: slot k holds element h_perm[k] of the caller's numbering
+    std::vector<uint4> tmp(m->view.nnz);
+    CK(cudaMemcpy(tmp.data(), m->view.elements, sizeof(uint4) * m->view.nnz, cudaMemcpyDeviceToHost));
+    uint4 *out = static_cast<uint4 *>(elements_out);
+    for (uint32_t k = 0; k < m->view.nnz; k++) out[m->h_perm[k]] = tmp[k];
+  }
   return 0;
 }
 
@@ -1394,7 +1423,7 @@ int abft_cuda_coo_flip_bit(abft_ctx *c, abft_coo_matrix *m, int index, int bit) 
   REQUIRE(bit >= 0 && bit < 128, "bit out of range");
   REQUIRE(index >= 0 && (uint32_t)index < m->view.nnz, "element index out of range");
   CK(cudaSetDevice(c->device));
-  coo_flip_bit_kernel<<<1, 32, 0, c->stream>>>(m->view.elements, (uint32_t)index, bit);
+  coo_flip_bit_kernel<<<1, 32, 0, c->stream>>>(m->view.elements, (uint32_t)index, bit, m->view.pos);
   c->launches++;
   c->epoch++;
   CK(cudaGetLastError());

@@ -18,6 +18,12 @@
 // recomputes the output entries the strays now point at, merging them into those groups by element index.
 // Result: the reference's result[] in every case the reference defines (it reads/writes out of bounds when
 // an index leaves [0, N): such an element is dropped here and in the oracle).
+//
+// GROUPED layout (opt-in at create_matrix, ABFT_CUDA_COO_LAYOUT=grouped; logic checked on the CPU, not yet run or timed
+// on a GPU): the elements are STORED in group order -- slot k of `perm` -- so thread c streams its group with
+// consecutive 128-bit loads instead of gathering 16-byte elements through `perm` (which is then only read to name an
+// element in a fault record); `pos` (element index -> slot) serves inject_bitflip, the CONSTRAINTS neighbour and the
+// stray fix-up.  Everything observable keeps the caller's numbering: fault indices, abft_cuda_coo_matrix_read.
 #pragma once
 #include "common.cuh"
 
@@ -85,7 +91,8 @@ __device__ __forceinline__ uint32_t &coo_word(uint4 &e, uint32_t w) {
 // generate_ecc_bits (COO/CPUContext.cpp:196-199 SED, 230-233 SEC7, 269-273 SEC8, 320-324 SECDED)
 __global__ void __launch_bounds__(kBlock)
 coo_encode_kernel(int mode, const uint32_t *__restrict__ cols, const uint32_t *__restrict__ rows,
-                  const double *__restrict__ values, uint4 *__restrict__ elements, uint32_t nnz) {
+                  const double *__restrict__ values, uint4 *__restrict__ elements, uint32_t nnz,
+                  const uint32_t *__restrict__ pos = nullptr /* grouped layout: element index -> slot */) {
   const uint32_t stride = gridDim.x * kBlock;
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nnz; i += stride) {
     const double v = values[i];
@@ -98,14 +105,14 @@ coo_encode_kernel(int mode, const uint32_t *__restrict__ cols, const uint32_t *_
       e.x |= coo_syndrome(e);
       e.x |= coo_overall(e) << 24;
     }
-    elements[i] = e;
+    elements[pos ? pos[i] : i] = e;
   }
 }
 
 // the 4-byte read-modify-write of inject_bitflip (COO/CPUContext.cpp:138)
-__global__ void coo_flip_bit_kernel(uint4 *elements, uint32_t index, int bit) {
+__global__ void coo_flip_bit_kernel(uint4 *elements, uint32_t index, int bit, const uint32_t *pos = nullptr) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  reinterpret_cast<uint32_t *>(elements + index)[bit / 32] ^= 1u << (bit % 32);
+  reinterpret_cast<uint32_t *>(elements + (pos ? pos[index] : index))[bit / 32] ^= 1u << (bit % 32);
 }
 
 constexpr uint32_t kMaxStray = 1024;
@@ -132,26 +139,35 @@ struct CooView {
   const uint32_t *colptr;  // [N+1] group boundaries in perm
   uint32_t *stray;         // [1 + kMaxStray]: count, then element indices (see the file comment)
   uint32_t N, nnz;
+  const uint32_t *pos;     // grouped layout only: [nnz] element index -> slot in `elements` (= slot in perm); else null
 };
+
+// where element i (caller's numbering) is stored
+template <bool GROUPED>
+__device__ __forceinline__ uint32_t coo_slot_of(const CooView &A, uint32_t i) { return GROUPED ? A.pos[i] : i; }
 
 // Check (and repair) one element the way the mode's spmv does; logs what the reference prints.
 // Returns false if the reference would have exit(1)ed at this element.
-template <int MODE>
-__device__ __forceinline__ bool coo_check(uint4 &e, uint32_t i, const CooView &A, const LogRef &L) {
+// `ph`: where the element is stored; `k`: its slot in perm (grouped layout: ph == k and the element's index in the
+// caller's numbering, which the fault records carry, is perm[k] -- only read when something is reported).
+template <int MODE, bool GROUPED>
+__device__ __forceinline__ bool coo_check(uint4 &e, uint32_t ph, uint32_t k, const CooView &A, const LogRef &L) {
+  if (MODE == ABFT_MODE_NONE) return true;
   if (MODE == ABFT_MODE_CONSTRAINTS) {
+    const uint32_t i = GROUPED ? A.perm[k] : ph;
     // COO/CPUContext.cpp:155-187, in the reference's order; the first violation is fatal.  (`bit` carries the
     // index so that the host orders these among themselves by element; it is cleared before reporting.)
     if (e.y >= A.N) { log_event(L, ABFT_EV_ROW_SIZE, i, 0); return false; }
     if (e.x >= A.N) { log_event(L, ABFT_EV_COL_SIZE, i, i); return false; }
     if (i + 1 < A.nnz) {
-      const uint4 nx = A.elements[i + 1];
+      const uint4 nx = A.elements[coo_slot_of<GROUPED>(A, i + 1)];
       if (e.y > nx.y) { log_event(L, ABFT_EV_ROW_ORDER, i, 0); return false; }
       if (e.y == nx.y && e.x >= nx.x) { log_event(L, ABFT_EV_COL_ORDER, i, i); return false; }
     }
     return true;
   }
   if (MODE == ABFT_MODE_SED) {
-    if (coo_overall(e)) { log_event(L, ABFT_EV_SED_DETECTED, i, 0); return false; }
+    if (coo_overall(e)) { log_event(L, ABFT_EV_SED_DETECTED, GROUPED ? A.perm[k] : ph, 0); return false; }
     return true;
   }
   if (MODE == ABFT_MODE_SEC7 || MODE == ABFT_MODE_SEC8 || MODE == ABFT_MODE_SECDED) {
@@ -159,6 +175,7 @@ __device__ __forceinline__ bool coo_check(uint4 &e, uint32_t i, const CooView &A
     if (MODE == ABFT_MODE_SEC8 && !odd) return true;  // the syndrome is only looked at when the parity trips
     const uint32_t s = coo_syndrome(e);
     const bool repair = (MODE == ABFT_MODE_SEC7) ? (s != 0) : (odd != 0);
+    const uint32_t i = GROUPED ? ((repair || s) ? A.perm[k] : 0u) : ph;  // (grouped: only looked up when something is reported)
     if (repair) {
       if (s) {
         const uint32_t bit = coo_flipped_bit(s);
@@ -169,7 +186,7 @@ __device__ __forceinline__ bool coo_check(uint4 &e, uint32_t i, const CooView &A
         e.x ^= 1u << 24;
         log_event(L, ABFT_EV_CORRECTED_PARITY, i, 0);
       }
-      A.elements[i] = e;  // mat->elements[i] = element (COO/CPUContext.cpp:254, 311, 363)
+      A.elements[ph] = e;  // mat->elements[i] = element (COO/CPUContext.cpp:254, 311, 363)
     } else if (MODE == ABFT_MODE_SECDED && s) {
       log_event(L, ABFT_EV_DOUBLE_BIT, i, 0);
       return false;
@@ -187,7 +204,7 @@ __device__ __forceinline__ double coo_value(const uint4 &e) { return __hiloint2d
 
 // result[c] = sum over group c, in element order, of value * vec[row]   (separate multiply and add: no FMA,
 // like the reference build)
-template <int MODE>
+template <int MODE, bool GROUPED>
 __global__ void __launch_bounds__(kBlock)
 coo_spmv_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ result, LogRef L) {
   const uint32_t stride = gridDim.x * kBlock;
@@ -195,14 +212,14 @@ coo_spmv_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ 
     double sum = 0.0;
     const uint32_t kb = A.colptr[c], ke = A.colptr[c + 1];
     for (uint32_t k = kb; k < ke; k++) {
-      const uint32_t i = A.perm[k];
-      uint4 e = A.elements[i];
-      if (!coo_check<MODE>(e, i, A, L)) continue;  // fatal at this element: the host stops at the first one in index order
+      const uint32_t ph = GROUPED ? k : A.perm[k];  // grouped: the group is stored in place, in order
+      uint4 e = A.elements[ph];
+      if (!coo_check<MODE, GROUPED>(e, ph, k, A, L)) continue;  // fatal at this element: the host stops at the first one in index order
       const uint32_t col = coo_out_index<MODE>(e);
       if (col != c) {
         // the element no longer belongs to this output entry: leave it to the fix-up kernel
         const uint32_t slot = atomicAdd(&A.stray[0], 1u);
-        if (slot < kMaxStray) A.stray[1 + slot] = i;
+        if (slot < kMaxStray) A.stray[1 + slot] = GROUPED ? A.perm[k] : ph;
         continue;
       }
       if (e.y >= A.N) continue;  // vec[] would be read out of bounds (UB in the reference): dropped, as in the oracle
@@ -215,16 +232,17 @@ coo_spmv_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ 
 // One thread.  For every output entry a stray element now points at: recompute that entry from its own
 // group (minus the members that strayed away) and the strays that target it, in ascending element index.
 // The elements were already checked / repaired by coo_spmv_kernel; nothing is logged here.
-template <int MODE>
+template <int MODE, bool GROUPED>
 __global__ void coo_stray_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ result) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const uint32_t n = min(A.stray[0], kMaxStray);
   A.stray[0] = 0;
   for (uint32_t s = 0; s < n; s++) {
-    const uint32_t target = coo_out_index<MODE>(A.elements[A.stray[1 + s]]);
+    const uint32_t target = coo_out_index<MODE>(A.elements[coo_slot_of<GROUPED>(A, A.stray[1 + s])]);
     if (target >= A.N) continue;  // result[] would be written out of bounds (UB in the reference): dropped
     bool seen = false;            // this target was recomputed for an earlier stray
-    for (uint32_t q = 0; q < s && !seen; q++) seen = coo_out_index<MODE>(A.elements[A.stray[1 + q]]) == target;
+    for (uint32_t q = 0; q < s && !seen; q++)
+      seen = coo_out_index<MODE>(A.elements[coo_slot_of<GROUPED>(A, A.stray[1 + q])]) == target;
     if (seen) continue;
     double sum = 0.0;
     uint32_t k = A.colptr[target];
@@ -236,19 +254,19 @@ __global__ void coo_stray_kernel(CooView A, const double *__restrict__ vec, doub
       uint32_t gi = 0xFFFFFFFFu;
       while (k < ke) {
         const uint32_t i = A.perm[k];
-        if (coo_out_index<MODE>(A.elements[i]) == target) { gi = i; break; }
+        if (coo_out_index<MODE>(A.elements[GROUPED ? k : i]) == target) { gi = i; break; }
         k++;
       }
       // smallest stray index >= last that targets this entry
       uint32_t si = 0xFFFFFFFFu;
       for (uint32_t q = 0; q < n; q++) {
         const uint32_t i = A.stray[1 + q];
-        if ((first || i >= last) && i < si && coo_out_index<MODE>(A.elements[i]) == target) si = i;
+        if ((first || i >= last) && i < si && coo_out_index<MODE>(A.elements[coo_slot_of<GROUPED>(A, i)]) == target) si = i;
       }
       const uint32_t i = min(gi, si);
       if (i == 0xFFFFFFFFu) break;
       if (i == gi) k++;
-      const uint4 e = A.elements[i];
+      const uint4 e = A.elements[coo_slot_of<GROUPED>(A, i)];
       if (e.y < A.N) sum = __dadd_rn(sum, __dmul_rn(coo_value(e), vec[e.y]));
       last = i + 1;
       first = false;

@@ -13,7 +13,8 @@ namespace {
 struct Emu {
   int mode = 0;
   std::vector<uint4> elements;
-  std::vector<uint32_t> perm, colptr, stray;
+  std::vector<uint32_t> perm, colptr, stray, pos;
+  bool grouped = false;
   DevLog log;
   unsigned int flag = 0;
   CooView view{};
@@ -35,16 +36,22 @@ template <int MODE>
 void spmv_mode(Emu *e, const double *vec, double *result) {
   LogRef L{&e->log, &e->flag};
   const int grid = std::max(1, std::min((int)((e->view.N + kBlock - 1) / kBlock), 3));  // few CTAs: exercises the grid stride
-  run_grid(grid, kBlock, [&] { coo_spmv_kernel<MODE>(e->view, vec, result, L); });
-  run_grid(1, 32, [&] { coo_stray_kernel<MODE>(e->view, vec, result); });
+  if (e->grouped) {
+    run_grid(grid, kBlock, [&] { coo_spmv_kernel<MODE, true>(e->view, vec, result, L); });
+    run_grid(1, 32, [&] { coo_stray_kernel<MODE, true>(e->view, vec, result); });
+  } else {
+    run_grid(grid, kBlock, [&] { coo_spmv_kernel<MODE, false>(e->view, vec, result, L); });
+    run_grid(1, 32, [&] { coo_stray_kernel<MODE, false>(e->view, vec, result); });
+  }
 }
 }  // namespace
 
 extern "C" {
 
-void *emu_create(int mode, const uint32_t *cols, const uint32_t *rows, const double *vals, int N, int nnz) {
+void *emu_create(int mode, const uint32_t *cols, const uint32_t *rows, const double *vals, int N, int nnz, int grouped) {
   Emu *e = new Emu();
   e->mode = mode;
+  e->grouped = grouped != 0 && nnz > 0;
   e->elements.resize((size_t)std::max(nnz, 1));
   e->perm.resize((size_t)std::max(nnz, 1));
   e->colptr.resize((size_t)N + 1);
@@ -54,22 +61,36 @@ void *emu_create(int mode, const uint32_t *cols, const uint32_t *rows, const dou
     delete e;
     return nullptr;
   }
-  run_grid(2, kBlock, [&] { coo_encode_kernel(mode, cols, rows, vals, e->elements.data(), (uint32_t)nnz); });
+  if (e->grouped) {
+    e->pos.resize((size_t)nnz);
+    for (int k = 0; k < nnz; k++) e->pos[e->perm[(size_t)k]] = (uint32_t)k;
+  }
+  const uint32_t *pos = e->grouped ? e->pos.data() : nullptr;
+  run_grid(2, kBlock, [&] { coo_encode_kernel(mode, cols, rows, vals, e->elements.data(), (uint32_t)nnz, pos); });
   e->view.elements = e->elements.data();
   e->view.perm = e->perm.data();
   e->view.colptr = e->colptr.data();
   e->view.stray = e->stray.data();
   e->view.N = (uint32_t)N;
   e->view.nnz = (uint32_t)nnz;
+  e->view.pos = pos;
   return e;
 }
 
 void emu_destroy(void *h) { delete (Emu *)h; }
-void *emu_elements(void *h) { return ((Emu *)h)->elements.data(); }
+// the elements in the caller's numbering (what abft_cuda_coo_matrix_read hands back), in a buffer owned by the emulator
+void *emu_elements(void *h) {
+  Emu *e = (Emu *)h;
+  if (!e->grouped) return e->elements.data();
+  static std::vector<uint4> out;
+  out.resize(e->elements.size());
+  for (size_t k = 0; k < (size_t)e->view.nnz; k++) out[e->perm[k]] = e->elements[k];
+  return out.data();
+}
 
 void emu_flip(void *h, int index, int bit) {
   Emu *e = (Emu *)h;
-  run_grid(1, 32, [&] { coo_flip_bit_kernel(e->elements.data(), (uint32_t)index, bit); });
+  run_grid(1, 32, [&] { coo_flip_bit_kernel(e->elements.data(), (uint32_t)index, bit, e->view.pos); });
 }
 
 // returns the number of raw (unsorted) log records copied to out[0..cap)

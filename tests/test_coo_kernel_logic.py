@@ -27,8 +27,9 @@ class Event(C.Structure):
     _fields_ = [("kind", C.c_int32), ("index", C.c_uint32), ("bit", C.c_uint32)]
 
 
-@pytest.fixture(scope="module")
-def EMU(tmp_path_factory):
+@pytest.fixture(scope="module", params=["caller_order", "grouped"])
+def EMU(request, tmp_path_factory):
+    """Both element layouts (coo.cuh): the shipped one and the opt-in grouped one (ABFT_CUDA_COO_LAYOUT=grouped)."""
     so = str(tmp_path_factory.mktemp("emu") / "libcoo_emul.so")
     h = os.path.join(ROOT, "tests", "helpers")
     subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-I" + os.path.join(h, "cuda_shim"),
@@ -37,13 +38,14 @@ def EMU(tmp_path_factory):
     u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
     f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
     L.emu_create.restype = C.c_void_p
-    L.emu_create.argtypes = [C.c_int, u32p, u32p, f64p, C.c_int, C.c_int]
+    L.emu_create.argtypes = [C.c_int, u32p, u32p, f64p, C.c_int, C.c_int, C.c_int]
     L.emu_destroy.argtypes = [C.c_void_p]
     L.emu_elements.restype = C.c_void_p
     L.emu_elements.argtypes = [C.c_void_p]
     L.emu_flip.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.emu_spmv.restype = C.c_int
     L.emu_spmv.argtypes = [C.c_void_p, f64p, f64p, C.POINTER(Event), C.c_int]
+    L.grouped = int(request.param == "grouped")
     return L
 
 
@@ -59,7 +61,7 @@ class EmuMatrix:
         self.L, self.mode, self.N, self.nnz = L, mode, t.N, int(t.cols.shape[0])
         self.h = L.emu_create(MODES.index(mode), np.ascontiguousarray(t.cols, dtype=np.uint32),
                               np.ascontiguousarray(t.rows, dtype=np.uint32), np.ascontiguousarray(t.vals, dtype=np.float64),
-                              t.N, self.nnz)
+                              t.N, self.nnz, getattr(L, "grouped", 0))
         assert self.h
 
     @property

@@ -23,8 +23,16 @@ for st in "${stages[@]}"; do
     ab)
       tools/ab_variants.sh run 50 > gpurun_out/session_ab.txt 2>&1; echo "ab kit: rc=$?"; tail -40 gpurun_out/session_ab.txt ;;
     coo)
-      python tools/time_spmv.py --workload poisson3d --format coo --modes none,sed,sec7,secded --reps 30 --warm 50 \
-          > gpurun_out/session_coo.jsonl 2> gpurun_out/session_coo.err; echo "coo timings: rc=$?"; cat gpurun_out/session_coo.jsonl ;;
+      # the opt-in grouped element layout (coo.cuh): parity first, then both layouts timed
+      ABFT_CUDA_COO_LAYOUT=grouped python -m pytest tests/test_gpu_coo.py -q -m gpu > gpurun_out/session_pytest_coo_grouped.txt 2>&1
+      echo "COO tests, grouped layout: rc=$?"; tail -2 gpurun_out/session_pytest_coo_grouped.txt
+      : > gpurun_out/session_coo.jsonl
+      for layout in caller grouped; do
+        ABFT_CUDA_COO_LAYOUT=$layout python tools/time_spmv.py --workload poisson3d --format coo --modes none,sed,sec7,secded \
+            --reps 30 --warm 50 --tag "coo_$layout" >> gpurun_out/session_coo.jsonl 2>> gpurun_out/session_coo.err
+        echo "coo timings ($layout): rc=$?"
+      done
+      cat gpurun_out/session_coo.jsonl ;;
     c5)
       for m in sec7 constraints; do
         python bench.py --workload powerlaw --mode $m --steps 100 --warmup 10 --all-modes 0 \
