@@ -72,13 +72,14 @@ namespace emu {
 struct Cta {
   explicit Cta(int n) : cta(n) {
     for (int w = 0; w < (n + 31) / 32; w++) warp.emplace_back(new std::barrier<>(std::min(32, n - 32 * w)));
-    xchg.assign((size_t)((n + 31) / 32) * 32, 0);
+    xchg.assign((size_t)((n + 31) / 32) * 32 * 2, 0);  // two buffers, see warp_exchange
   }
   std::barrier<> cta;
   std::vector<std::unique_ptr<std::barrier<>>> warp;
   std::vector<uint64_t> xchg;
 };
 static Cta *g_cta = nullptr;
+static thread_local unsigned t_phase = 0;  // collectives this thread has made in the running CTA (see warp_exchange)
 
 // run `grid` CTAs one after the other, each as `block` real threads (a persistent pool: thread creation would
 // otherwise dominate the run time of the tests)
@@ -105,6 +106,7 @@ struct Pool {
       }
       blockIdx.x = (unsigned)b;
       threadIdx.x = (unsigned)t;
+      t_phase = 0;
       (*f)();
       std::lock_guard<std::mutex> lk(m);
       if (--remaining == 0) done.notify_all();
@@ -141,30 +143,29 @@ static void launch(int grid, int block, F f) {
   }
 }
 
-// full-mask warp exchange: everyone publishes, everyone reads, and nobody overwrites before all have read
+// full-mask warp exchange: everyone publishes, one barrier, everyone reads.  Two buffers used alternately (each
+// thread counts its own collectives, and all lanes of a warp make the same ones): a slot is only written again two
+// collectives later, i.e. after a barrier that every reader of the old value has passed.
 template <class T>
 static inline T warp_exchange(T mine, int src_lane_of_me) {
   static_assert(sizeof(T) <= 8, "exchange slot is 8 bytes");
   const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+  uint64_t *buf = g_cta->xchg.data() + (size_t)(t_phase++ & 1u) * g_cta->xchg.size() / 2 + (size_t)warp * 32;
   uint64_t raw = 0;
   memcpy(&raw, &mine, sizeof(T));
-  g_cta->xchg[(size_t)warp * 32 + lane] = raw;
+  buf[lane] = raw;
   g_cta->warp[warp]->arrive_and_wait();
   T out = mine;
-  if (src_lane_of_me >= 0 && src_lane_of_me < 32) {
-    const uint64_t got = g_cta->xchg[(size_t)warp * 32 + src_lane_of_me];
-    memcpy(&out, &got, sizeof(T));
-  }
-  g_cta->warp[warp]->arrive_and_wait();
+  if (src_lane_of_me >= 0 && src_lane_of_me < 32) memcpy(&out, &buf[src_lane_of_me], sizeof(T));
   return out;
 }
 static inline uint32_t warp_ballot(bool pred) {
   const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
-  g_cta->xchg[(size_t)warp * 32 + lane] = pred ? 1u : 0u;
+  uint64_t *buf = g_cta->xchg.data() + (size_t)(t_phase++ & 1u) * g_cta->xchg.size() / 2 + (size_t)warp * 32;
+  buf[lane] = pred ? 1u : 0u;
   g_cta->warp[warp]->arrive_and_wait();
   uint32_t m = 0;
-  for (int l = 0; l < 32; l++) m |= (uint32_t)(g_cta->xchg[(size_t)warp * 32 + l] & 1u) << l;
-  g_cta->warp[warp]->arrive_and_wait();
+  for (int l = 0; l < 32; l++) m |= (uint32_t)(buf[l] & 1u) << l;
   return m;
 }
 
