@@ -382,3 +382,35 @@ def test_crc_chunk_table_variant(tmp_path_factory, pkg, O, chunk, walk):
             for arr, clean in ((em.cols, clean_c), (om.cols, clean_c), (em.values, clean_v), (om.values, clean_v)):
                 arr[index] = clean[index]
         em.close()
+
+
+def test_cg_trajectory_with_the_emulated_kernels(EMU, pkg, O):
+    """cg.cpp:83-118 driven over the emulated spmv (with its fused dot), calc_xr and calc_p -- tree reductions and all --
+    against the oracle's sequential loop: one injected flip is repaired on the way, the iteration count is equal and
+    the residual history agrees to 1e-10 relative (the tolerance BASELINE.json states for reordered reductions)."""
+    t = pkg.matgen.poisson2d(24)
+    b = pkg.matgen.rhs(t.N)
+    N = t.N
+    em = EmuMatrix(EMU, pkg, "secded", t)
+    om = O.OracleMatrix("secded", t.cols, t.rows, t.vals, t.N)
+    em.flip(1234, 37)
+    om.flip(1234, 37)
+    ref = om.cg(b, 500, 1e-10)
+    x, r, p = np.zeros(N), b.copy(), b.copy()
+    rr = EMU.emu_dot(em.h, r, r, N, 3)
+    hist, lines = [], []
+    for itr in range(500):
+        if rr <= 1e-10:
+            break
+        w, fatal, events, pw = em.spmv(p)
+        assert not fatal
+        lines += [O.format_event(*e) for e in events]
+        rr_new = EMU.emu_calc_xr(em.h, x, r, p, w, rr / pw, N, 3)
+        EMU.emu_calc_p(p, r, rr_new / rr, N, 3)
+        rr = rr_new
+        hist.append(rr)
+    assert lines == [O.format_event(*e) for e in ref["events"]] == ["[ECC] corrected bit 37 at index 1234"]
+    assert len(hist) == ref["iterations"]
+    assert np.max(np.abs(np.array(hist) - ref["rr_hist"]) / ref["rr_hist"]) <= 1e-10
+    assert np.max(np.abs(x - ref["x"])) <= 1e-9 * np.max(np.abs(ref["x"]))
+    em.close()
