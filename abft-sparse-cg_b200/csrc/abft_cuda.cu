@@ -181,7 +181,7 @@ int abft_cuda_device_count(void) {
 }
 
 int abft_cuda_event_is_fatal(int kind) {
-  return !(kind == ABFT_EV_CORRECTED_BIT || kind == ABFT_EV_CORRECTED_PARITY);
+  return !(kind == ABFT_EV_CORRECTED_BIT || kind == ABFT_EV_CORRECTED_PARITY || kind == ABFT_EV_ROWPTR_CORRECTED);
 }
 
 int abft_cuda_format_event(const abft_event *e, char *buf, int buflen) {
@@ -195,6 +195,8 @@ int abft_cuda_format_event(const abft_event *e, char *buf, int buflen) {
     case ABFT_EV_COL_SIZE: return snprintf(buf, buflen, "column size constraint violated at index %d", (int)e->index);
     case ABFT_EV_COL_ORDER: return snprintf(buf, buflen, "column order constraint violated at index %d", (int)e->index);
     case ABFT_EV_CRC_ROW: return snprintf(buf, buflen, "[CRC32C] error detected in row %d", (int)e->index);
+    case ABFT_EV_ROWPTR_CORRECTED: return snprintf(buf, buflen, "[ROWS] corrected bit %u of row pointer pair %d", e->bit, (int)e->index);
+    case ABFT_EV_ROWPTR_DOUBLE: return snprintf(buf, buflen, "[ROWS] double-bit error detected in row pointer pair %d", (int)e->index);
     default: return snprintf(buf, buflen, "unknown event %d", (int)e->kind);
   }
 }
@@ -395,10 +397,40 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
     c->launches++;
   }
   CKP(cudaGetLastError());
+#if ABFT_ROWS_ECC
+  bool protect_rows = false;
+#endif
+  {
+    const char *pr = getenv("ABFT_CUDA_PROTECT_ROWS");
+    if (pr && *pr && strcmp(pr, "0") && strcmp(pr, "none")) {
+#if ABFT_ROWS_ECC
+      if (strcmp(pr, "secded") || nnz >= (1 << 28) || (row_offset & 1)) {
+        fail(-1, "ABFT_CUDA_PROTECT_ROWS: only `secded` exists; it needs nnz < 2^28 and partitions that start on even rows",
+             __FILE__, __LINE__);
+        return nullptr;
+      }
+      protect_rows = true;
+#else
+      fail(-1, "ABFT_CUDA_PROTECT_ROWS: this library was built without row-pointer protection (-DABFT_ROWS_ECC=1)",
+           __FILE__, __LINE__);
+      return nullptr;
+#endif
+    }
+  }
   // tiles: greedy over the row pointers (host, O(rows))
   std::vector<uint32_t> h_rowptr((size_t)n_rows + 1);
   CKP(cudaMemcpyAsync(h_rowptr.data(), m->d_rowptr, sizeof(uint32_t) * ((size_t)n_rows + 1), cudaMemcpyDeviceToHost,
                       c->stream));
+#if ABFT_ROWS_ECC
+  if (protect_rows) {
+    // (after the plain pointers went to the host for the tile plan)
+    const uint32_t n_words = ((uint32_t)n_rows + 1u + 1u) & ~1u;
+    encode_rowptr_pairs_kernel<<<grid, kBlock, 0, c->stream>>>(m->d_rowptr, n_words);
+    c->launches++;
+    CKP(cudaGetLastError());
+    m->view.rows_ecc = 1u;
+  }
+#endif
   CKP(cudaStreamSynchronize(c->stream));
   CKP(cudaFree(d_coo_rows));
   d_coo_rows = nullptr;
@@ -843,7 +875,11 @@ int abft_cuda_poll_events(abft_ctx *c, abft_event *out, int cap, int *fatal) {
       k3 = e.bit;
     }
   };
+  auto rowptr_ev = [](const abft_event &e) { return e.kind == ABFT_EV_ROWPTR_CORRECTED || e.kind == ABFT_EV_ROWPTR_DOUBLE; };
   std::sort(ev.begin(), ev.end(), [&](const abft_event &a, const abft_event &b) {
+    // the row pointers are checked before the kernel looks at them: their events come first, by pair (rowsecc.cuh)
+    if (rowptr_ev(a) != rowptr_ev(b)) return rowptr_ev(a);
+    if (rowptr_ev(a)) return a.index != b.index ? a.index < b.index : a.kind < b.kind;
     uint64_t a1, a3, b1, b3;
     int a2, b2;
     key(a, a1, a2, a3);

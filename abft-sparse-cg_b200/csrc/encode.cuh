@@ -70,6 +70,18 @@ encode_crc_rows_kernel(const uint32_t *__restrict__ rowptr, uint32_t *__restrict
   }
 }
 
+// row-pointer protection (rowsecc.cuh): check bits into bits 28..31 of every pair {rowptr[2k], rowptr[2k+1]};
+// n_words is even (the array is padded with zeros, which the last pair may include)
+__global__ void __launch_bounds__(kBlock) encode_rowptr_pairs_kernel(uint32_t *__restrict__ rowptr, uint32_t n_words) {
+  const uint32_t stride = gridDim.x * kBlock;
+  for (uint32_t k = 2 * (blockIdx.x * kBlock + threadIdx.x); k + 1 < n_words; k += 2 * stride) {
+    uint32_t w0 = rowptr[k], w1 = rowptr[k + 1];
+    rows_encode_pair(w0, w1);
+    rowptr[k] = w0;
+    rowptr[k + 1] = w1;
+  }
+}
+
 // the 4-byte read-modify-write of inject_bitflip (CSR/CPUContext.cpp:150-157)
 __global__ void flip_bit_kernel(uint32_t *cols, double *values, uint32_t index, int bit) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;

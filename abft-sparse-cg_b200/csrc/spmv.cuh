@@ -34,6 +34,7 @@
 #pragma once
 #include "common.cuh"
 #include "ecc.cuh"
+#include "rowsecc.cuh"
 
 namespace abft {
 
@@ -83,6 +84,9 @@ struct MatView {
   uint32_t n_cols;      // global N: bound for the gather
   uint32_t row_offset;  // global index of local row 0
   uint32_t nnz_offset;  // global index of local element 0 (for reported indices)
+#if ABFT_ROWS_ECC
+  uint32_t rows_ecc;    // rowptr[] carries the SECDED pair code of rowsecc.cuh (check bits in bits 28..31)
+#endif
 };
 
 // one pipeline stage of staged tile data (windows start at 16-byte aligned indices)
@@ -613,6 +617,33 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     if (DYN && t.info == kTileNone) break;
     const bool irregular_tile = !(t.info & (kTileLongRow | kTileRegular)) && MODE != ABFT_MODE_CRC32C;
     const StageBuf &B = stage[st];
+#if ABFT_ROWS_ECC
+    if (A.rows_ecc) {
+      // Protected row pointers (rowsecc.cuh): check every pair of the staged window before anyone looks at it, repair
+      // single flips (in the stage and in global memory), strip the check bits.  After the barrier the stage holds
+      // plain pointers and the rest of the kernel is unchanged.  The window starts and ends on multiples of four
+      // pointers, so pairs are never split; words past rows[n_rows] are zero padding (a valid code word).
+      uint32_t *rp = const_cast<uint32_t *>(B.rptr);
+      const uint32_t wb = t.row_begin & ~3u;
+      const uint32_t n_words = ((t.row_begin + (t.info & 0xFFFFu) + 1 + 3) & ~3u) - wb;
+      for (uint32_t k = 2 * tid; k + 1 < n_words; k += 2 * kBlock) {
+        uint32_t w0 = rp[k], w1 = rp[k + 1], bit = 0;
+        const int verdict = rows_check_pair(w0, w1, &bit);
+        const uint32_t pair = (A.row_offset + wb + k) / 2;   // (partitions start on even rows when protected)
+        if (verdict == 1) {
+          log_event(L, ABFT_EV_ROWPTR_CORRECTED, pair, bit);
+          uint32_t *g = const_cast<uint32_t *>(A.rowptr) + wb + k;
+          g[0] = w0;
+          g[1] = w1;
+        } else if (verdict == 2) {
+          log_event(L, ABFT_EV_ROWPTR_DOUBLE, pair, 0);
+        }
+        rp[k] = w0 & kRowsDataMask;
+        rp[k + 1] = w1 & kRowsDataMask;
+      }
+      __syncthreads();
+    }
+#endif
     if (dynamic) dot_part = 0.0;  // reduced per tile below
     const uint32_t nrows = t.info & 0xFFFFu;
     const uint32_t n = t.nnz_end - t.nnz_begin;

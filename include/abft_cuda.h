@@ -55,7 +55,10 @@ enum abft_event_kind {
   ABFT_EV_ROW_ORDER = 6,        /* "row order constraint violated for row%d"       fatal */
   ABFT_EV_COL_SIZE = 7,         /* "column size constraint violated at index %d"   fatal */
   ABFT_EV_COL_ORDER = 8,        /* "column order constraint violated at index %d"  fatal */
-  ABFT_EV_CRC_ROW = 9           /* "[CRC32C] error detected in row %d"             fatal */
+  ABFT_EV_CRC_ROW = 9,          /* "[CRC32C] error detected in row %d"             fatal */
+  /* row-pointer protection (repository-defined, opt-in build: csrc/rowsecc.cuh); index = pair of row pointers */
+  ABFT_EV_ROWPTR_CORRECTED = 10, /* "[ROWS] corrected bit %u of row pointer pair %d"        */
+  ABFT_EV_ROWPTR_DOUBLE = 11     /* "[ROWS] double-bit error detected in row pointer pair %d" fatal */
 };
 
 typedef struct abft_event {

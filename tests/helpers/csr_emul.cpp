@@ -19,6 +19,7 @@ struct Emu {
   std::vector<double> vals;
   std::vector<Tile> tiles;
   bool dyn = false;
+  bool rows_ecc = false;
   unsigned int tile_counter = 0;
   DevLog log;
   unsigned int flag = 0;
@@ -61,6 +62,9 @@ void spmv_inst(Emu *e, const double *vec, double *result) {
   A.n_cols = e->n_cols;
   A.row_offset = 0;
   A.nnz_offset = 0;
+#if ABFT_ROWS_ECC
+  A.rows_ecc = e->rows_ecc ? 1u : 0u;
+#endif
   LogRef L{&e->log, &e->flag};
   const ReduceOut red = reduce_of(e);
   const int grid = std::max(1, std::min((int)e->tiles.size(), e->grid));
@@ -117,6 +121,20 @@ void emu_set_tiles(void *h, const uint32_t *recs, int n_tiles, int dyn, int grid
   for (int i = 0; i < n_tiles; i++) e->tiles[i] = Tile{recs[4 * i], recs[4 * i + 1], recs[4 * i + 2], recs[4 * i + 3]};
   e->dyn = dyn != 0;
   e->grid = grid;
+}
+
+// row-pointer protection (rowsecc.cuh), as abft_cuda_matrix_create_part applies it; 0 if not compiled in
+int emu_protect_rows(void *h) {
+#if ABFT_ROWS_ECC
+  Emu *e = (Emu *)h;
+  const uint32_t n_words = (e->n_rows + 1u + 1u) & ~1u;
+  emu::launch(2, kBlock, [&] { encode_rowptr_pairs_kernel(e->rowptr.data(), n_words); });
+  e->rows_ecc = true;
+  return 1;
+#else
+  (void)h;
+  return 0;
+#endif
 }
 
 uint32_t *emu_cols(void *h) { return ((Emu *)h)->cols.data(); }

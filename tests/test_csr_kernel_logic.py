@@ -19,7 +19,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"]
-FATAL = {1, 4, 5, 6, 7, 8, 9}          # every kind but CORRECTED_BIT (2) and CORRECTED_PARITY (3)
+FATAL = {1, 4, 5, 6, 7, 8, 9, 11}      # every kind but CORRECTED_BIT (2), CORRECTED_PARITY (3), ROWPTR_CORRECTED (10)
+ROWPTR_EVENTS = {10, 11}               # reported ahead of everything else, by pair (csrc/rowsecc.cuh)
 ROW_EVENTS = {5, 6, 9}                 # ROW_SIZE, ROW_ORDER, CRC_ROW
 REGULAR = 1 << 16
 SLOW = os.environ.get("ABFT_SLOW_TESTS") == "1"   # more modes / cases / variant combinations than the default run
@@ -123,7 +124,9 @@ class EmuMatrix:
         def key(e):
             kind, index, bit = e
             rowev = kind in ROW_EVENTS
-            return ((index if rowev else bit), (0 if rowev else 1), index, kind) if cons else (index, 0, bit, kind)
+            if kind in ROWPTR_EVENTS:
+                return (0, index, 0, 0, kind)
+            return (1,) + (((index if rowev else bit), (0 if rowev else 1), index, kind) if cons else (index, 0, bit, kind))
         raw = sorted(((log[i].kind, log[i].index, log[i].bit) for i in range(n)), key=key)
         events, fatal = [], False
         for kind, index, bit in raw:

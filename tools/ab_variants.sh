@@ -22,6 +22,7 @@ VARIANTS=(
   "crcwalk:-DABFT_CRC_WALK=1"
   "crcwalk6:-DABFT_CRC_WALK=1 -DABFT_CRC_CHUNK=6"
   "crcwalk5_t1536:-DABFT_CRC_WALK=1 -DABFT_CRC_CHUNK=5 -DABFT_TILE_STATIC=1536"
+  "rowsecc:-DABFT_ROWS_ECC=1"
 )
 case "${1:-}" in
   build)
@@ -44,7 +45,7 @@ case "${1:-}" in
       lib="$OUT/libabftcuda_$name.so"
       [ -f "$lib" ] || { echo "missing $lib (run: tools/ab_variants.sh build)"; continue; }
       # parity first: a variant that is not bit-exact is not timed
-      if ABFT_CUDA_LIB="$lib" python -m pytest "$ROOT/tests/test_gpu_parity.py" -x -q -m gpu > "$ROOT/gpurun_out/ab_parity_$name.txt" 2>&1; then
+      if ABFT_CUDA_LIB="$lib" python -m pytest "$ROOT/tests/test_gpu_parity.py" "$ROOT/tests/test_gpu_rowptr.py" -x -q -m gpu > "$ROOT/gpurun_out/ab_parity_$name.txt" 2>&1; then
         ABFT_CUDA_LIB="$lib" python "$ROOT/tools/time_spmv.py" --workload poisson3d --modes none,sec7,secded,crc32c \
             --reps "$reps" --tag "$name" >> "$ROOT/gpurun_out/ab_variants.jsonl"
       else
