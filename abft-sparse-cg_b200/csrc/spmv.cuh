@@ -476,6 +476,15 @@ struct WaitSpec {
 #ifndef ABFT_WALK_UNIFORM
 #define ABFT_WALK_UNIFORM 0
 #endif
+// experiment (opt-in, -DABFT_SPMV_LASTREFILL=1): no CTA barrier per tile in the static kernel.  Every
+// warp counts itself out of a stage when it has finished the tile in it; the warp that is LAST issues the refill of
+// that stage (tile + kStages), so nobody waits for anybody except for data.  Warps may drift up to a tile apart.
+#ifndef ABFT_SPMV_LASTREFILL
+#define ABFT_SPMV_LASTREFILL 0
+#endif
+#if ABFT_SPMV_LASTREFILL && ABFT_ROWS_ECC
+#error "the row-pointer pre-pass needs the per-tile CTA barrier: do not combine ABFT_ROWS_ECC with ABFT_SPMV_LASTREFILL"
+#endif
 #ifndef ABFT_SPMV_MINB
 #define ABFT_SPMV_MINB 4  // resident CTAs per SM the register allocation is tuned for
 #endif
@@ -496,6 +505,8 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   __shared__ __align__(8) uint64_t s_full[kStages];
   __shared__ Tile s_tile[kStages];
   __shared__ uint32_t s_tidx[kStages];              // index of the staged tile (dynamic schedule: its partial's slot)
+  __shared__ unsigned int s_done[kStages];          // ABFT_SPMV_LASTREFILL: warps that have finished the tile in a stage
+  constexpr bool last_refill = ABFT_SPMV_LASTREFILL && !DYN;
   __shared__ double s_wdot[2][kBlock / 32];         // dynamic schedule: the warps' dot() partials of a tile
   __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? kCrcSpmvWords : 1];
   __shared__ double s_warp[kBlock / 32];
@@ -566,14 +577,16 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   };
 
   if (tid == 0) {
-    for (int j = 0; j + 1 < kStages; j++) {
+    // (last_refill: every stage is filled up front; afterwards a stage is refilled by the warp that leaves it last)
+    for (int j = 0; j + (last_refill ? 0 : 1) < kStages; j++) {
       fetch_ahead();
       s_tile[j] = ahead;
       s_tidx[j] = ahead_idx;
+      s_done[j] = 0u;
       if (ahead.info != kTileNone) issue(j, ahead);
       else mbar_arrive(&s_full[j]);  // nothing to stream: complete the phase so the waiters get to see the marker
     }
-    fetch_ahead();
+    if (!last_refill) fetch_ahead();
   }
   if (wait.mask) {
     // the matrix stream of the first tile is already in flight; vec[] is only touched after this
@@ -593,7 +606,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   for (; DYN || it < n_my; it++) {
     const int st = (int)(it % kStages);
     // thread 0: bank the previous tile's dot() partial (dynamic schedule), refill the stage that tile released
-    if (tid == 0) {
+    if (tid == 0 && !last_refill) {
       if (dynamic && it > 0) {
         // the warps' sums, added in warp order
         const double *wd = s_wdot[(it - 1) & 1u];
@@ -948,7 +961,31 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
       const double wp = warp_sum(dot_part);
       if ((tid & 31) == 0) s_wdot[it & 1u][tid >> 5] = wp;
     }
-    __syncthreads();  // everyone is done with stage `st`: it may be refilled
+#if ABFT_SPMV_LASTREFILL
+    if (last_refill) {
+      // this warp is done with stage `st`; the warp that is last to say so refills it with tile it + kStages
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        __threadfence_block();  // (release: this warp's reads of the stage are behind it)
+        const unsigned int before = atomicAdd(&s_done[st], 1u);
+        if (before == kBlock / 32 - 1) {
+          __threadfence_block();  // (acquire: so are everybody else's)
+          s_done[st] = 0u;
+          const uint32_t nxt = it + kStages;
+          if (nxt < n_my) {
+            const uint32_t idx = blockIdx.x + nxt * G;
+            const Tile tn = A.tiles[idx];
+            s_tile[st] = tn;
+            s_tidx[st] = idx;
+            issue(st, tn);
+          }
+        }
+      }
+    } else
+#endif
+    {
+      __syncthreads();  // everyone is done with stage `st`: it may be refilled
+    }
   }
   if (dynamic && tid == 0 && it > 0) {
     // the last tile's dot() partial

@@ -84,6 +84,7 @@ int emu_tile_nnz(int dyn) { return dyn ? kTileNnzDyn : kTileNnz; }
 int emu_walk_uniform(void) { return ABFT_WALK_UNIFORM; }
 int emu_crc_chunk(void) { return ABFT_CRC_CHUNK; }
 int emu_crc_walk(void) { return ABFT_CRC_WALK; }
+int emu_last_refill(void) { return ABFT_SPMV_LASTREFILL; }
 
 // create_matrix as abft_cuda_matrix_create_part does it: row pointers and check bits by the device kernels
 void *emu_create(int mode, const uint32_t *cols, const uint32_t *coo_rows, const double *vals, int N, int nnz) {

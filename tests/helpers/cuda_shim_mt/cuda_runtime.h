@@ -63,6 +63,7 @@ template <class T> static inline T __ldg(const T *p) { return *p; }
 template <class T> static inline T __ldcs(const T *p) { return *p; }
 template <class T> static inline T __ldcg(const T *p) { return *p; }
 template <class T> static inline void __stcs(T *p, const T &v) { *p = v; }
+static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
@@ -223,6 +224,7 @@ static unsigned char *g_dyn_smem = nullptr;
 }  // namespace emu
 
 static inline void __syncthreads() { emu::g_cta->cta.arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::g_cta->warp[(int)threadIdx.x >> 5]->arrive_and_wait(); }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int delta) {
   const int lane = (int)threadIdx.x & 31;
   return emu::warp_exchange(v, lane + delta < 32 ? lane + delta : lane);

@@ -417,3 +417,40 @@ def test_cg_trajectory_with_the_emulated_kernels(EMU, pkg, O):
     assert np.max(np.abs(np.array(hist) - ref["rr_hist"]) / ref["rr_hist"]) <= 1e-10
     assert np.max(np.abs(x - ref["x"])) <= 1e-9 * np.max(np.abs(ref["x"]))
     em.close()
+
+
+@pytest.mark.parametrize("mode", ["none", "secded", "crc32c"])
+def test_last_refill_variant(tmp_path_factory, pkg, O, mode):
+    """-DABFT_SPMV_LASTREFILL=1 (static kernel without the per-tile CTA barrier: the warp that leaves a stage last refills
+    it): many tiles per CTA so that the stage ring turns over several times and warps drift apart; clean results bit for
+    bit, faults reported and repaired as before, rows longer than a tile (block-wide reductions in between) included."""
+    L = _build(tmp_path_factory.mktemp("csr_emu_lr"), "lastrefill", ["-DABFT_SPMV_LASTREFILL=1"])
+    assert L.emu_last_refill() == 1
+    rng = np.random.default_rng(41)
+    cases = {"p3d_16": pkg.matgen.poisson3d(16), "p2d_40": shapes(pkg.matgen)["p2d_40"](), "one": shapes(pkg.matgen)["one_by_one"]()}
+    if mode == "crc32c":
+        cases["long_rows"] = shapes(pkg.matgen)["long_rows"]()      # (static kernel in every case for this mode)
+    for name, t in cases.items():
+        for grid in (1, 3):
+            em = EmuMatrix(L, pkg, mode, t, grid=grid)
+            assert not em.dyn
+            om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+            vec = rng.standard_normal(t.N)
+            y, fatal, events, dot = em.spmv(vec)
+            y0, _, _ = om.spmv(vec)
+            lens = np.bincount(t.rows, minlength=t.N)
+            assert not fatal and events == [], (name, grid, events)
+            assert np.array_equal(y[lens <= 32].view(np.uint64), y0[lens <= 32].view(np.uint64)), (name, grid)
+            assert abs(dot - float(np.dot(vec, y))) <= 1e-10 * max(np.abs(vec * y).sum(), 1e-300)
+            if mode != "none" and t.nnz > 10:
+                for trial in range(3):
+                    index, bit = int(rng.integers(0, t.nnz)), int(rng.integers(0, 96))
+                    em.flip(index, bit)
+                    om.flip(index, bit)
+                    y, fatal, events, _ = em.spmv(vec)
+                    y0, fatal0, ev0 = om.spmv(vec)
+                    assert (fatal, events) == (fatal0, ev0), (name, grid, index, bit)
+                    if fatal:
+                        break
+                    assert np.array_equal(em.cols, om.cols), (name, grid, index, bit)
+            em.close()

@@ -5,7 +5,7 @@
 #   tools/ab_variants.sh run [reps]       # on the GPU box: parity tests + spmv timings per variant -> gpurun_out/ab_variants.jsonl
 #
 # Variants (name:flags).  `base` is the shipped configuration.  Knobs: spmv.cuh (ABFT_WALK_UNIFORM, ABFT_TILE_STATIC,
-# ABFT_TILE_DYN, ABFT_SPMV_MINB, ABFT_ELEM_BATCH, ABFT_CRC_CHUNK, ABFT_CRC_WALK).  A variant is only ever adopted after `run` shows it parity-green
+# ABFT_TILE_DYN, ABFT_SPMV_MINB, ABFT_ELEM_BATCH, ABFT_CRC_CHUNK, ABFT_CRC_WALK, ABFT_SPMV_LASTREFILL; ABFT_ROWS_ECC in rowsecc.cuh).  A variant is only ever adopted after `run` shows it parity-green
 # and faster; numbers taken here are kernel timings (CUDA events), not bench values.
 set -euo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
@@ -23,6 +23,8 @@ VARIANTS=(
   "crcwalk6:-DABFT_CRC_WALK=1 -DABFT_CRC_CHUNK=6"
   "crcwalk5_t1536:-DABFT_CRC_WALK=1 -DABFT_CRC_CHUNK=5 -DABFT_TILE_STATIC=1536"
   "rowsecc:-DABFT_ROWS_ECC=1"
+  "lastrefill:-DABFT_SPMV_LASTREFILL=1"
+  "uni_lastrefill:-DABFT_WALK_UNIFORM=1 -DABFT_SPMV_LASTREFILL=1"
 )
 case "${1:-}" in
   build)
