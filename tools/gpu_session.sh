@@ -32,7 +32,12 @@ for st in "${stages[@]}"; do
             --reps 30 --warm 50 --tag "coo_$layout" >> gpurun_out/session_coo.jsonl 2>> gpurun_out/session_coo.err
         echo "coo timings ($layout): rc=$?"
       done
-      cat gpurun_out/session_coo.jsonl ;;
+      cat gpurun_out/session_coo.jsonl
+      for layout in caller grouped; do
+        python tools/bench_coo.py --mode secded --layout $layout --steps 100 --warmup 5 \
+            > gpurun_out/session_bench_coo_$layout.json 2> gpurun_out/session_bench_coo_$layout.err
+        echo "bench_coo ($layout): rc=$?"; cat gpurun_out/session_bench_coo_$layout.json
+      done ;;
     c5)
       for m in sec7 constraints; do
         python bench.py --workload powerlaw --mode $m --steps 100 --warmup 10 --all-modes 0 \
