@@ -7,6 +7,9 @@
 #   3 coo      COO spmv timings (tools/time_spmv.py --format coo)
 #   4 c5       bench.py --workload powerlaw at the size BASELINE names (N = 2^23, ~1.9e8 non-zeros), sec7 and constraints
 #   5 bench    the default bench line
+#   6 ncu      (not in the default list) `ncu --set full` of one spmv launch per mode named in $NCU_MODES (default
+#              "secded crc32c") with the library named by $ABFT_CUDA_LIB, reports under gpurun_out/ for tools/ncu_summary.py;
+#              plus the launch list of a short bench run.  Only after the same commands have run clean without ncu.
 # Usage: tools/gpu_session.sh [stage ...]   (default: all)
 set -uo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
@@ -45,6 +48,16 @@ for st in "${stages[@]}"; do
       done ;;
     bench)
       python bench.py > gpurun_out/session_bench.json 2> gpurun_out/session_bench.err; echo "bench: rc=$?"; cat gpurun_out/session_bench.json ;;
+    ncu)
+      for m in ${NCU_MODES:-secded crc32c}; do
+        python tools/prof_spmv.py --mode $m --reps 3 > /dev/null 2>&1 || { echo "prof_spmv $m failed without ncu: skipped"; continue; }
+        ncu --set full --clock-control none --import-source on -k regex:spmv_kernel -s 1 -c 1 -f \
+            -o gpurun_out/session_ncu_spmv_$m python tools/prof_spmv.py --mode $m --reps 3 > gpurun_out/session_ncu_spmv_$m.log 2>&1
+        echo "ncu spmv $m: rc=$?"
+      done
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/session_ncu_launches.csv \
+          python bench.py --steps 20 --warmup 3 --all-modes 0 --no-cpu-baseline > gpurun_out/session_ncu_launches.log 2>&1
+      echo "ncu launch list: rc=$?" ;;
     *) echo "unknown stage $st" ;;
   esac
 done
