@@ -204,6 +204,22 @@ __device__ __forceinline__ double coo_value(const uint4 &e) { return __hiloint2d
 
 // result[c] = sum over group c, in element order, of value * vec[row]   (separate multiply and add: no FMA,
 // like the reference build)
+// one element of group c: check / repair, then its product into `sum` (or onto the stray list, or nowhere)
+template <int MODE, bool GROUPED>
+__device__ __forceinline__ void coo_accumulate(uint4 e, uint32_t ph, uint32_t k, uint32_t c, const CooView &A,
+                                               const double *__restrict__ vec, const LogRef &L, double &sum) {
+  if (!coo_check<MODE, GROUPED>(e, ph, k, A, L)) return;  // fatal at this element: the host stops at the first one in index order
+  const uint32_t col = coo_out_index<MODE>(e);
+  if (col != c) {
+    // the element no longer belongs to this output entry: leave it to the fix-up kernel
+    const uint32_t slot = atomicAdd(&A.stray[0], 1u);
+    if (slot < kMaxStray) A.stray[1 + slot] = GROUPED ? A.perm[k] : ph;
+    return;
+  }
+  if (e.y >= A.N) return;  // vec[] would be read out of bounds (UB in the reference): dropped, as in the oracle
+  sum = __dadd_rn(sum, __dmul_rn(coo_value(e), vec[e.y]));
+}
+
 template <int MODE, bool GROUPED>
 __global__ void __launch_bounds__(kBlock)
 coo_spmv_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ result, LogRef L) {
@@ -211,19 +227,20 @@ coo_spmv_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ 
   for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < A.N; c += stride) {
     double sum = 0.0;
     const uint32_t kb = A.colptr[c], ke = A.colptr[c + 1];
-    for (uint32_t k = kb; k < ke; k++) {
-      const uint32_t ph = GROUPED ? k : A.perm[k];  // grouped: the group is stored in place, in order
-      uint4 e = A.elements[ph];
-      if (!coo_check<MODE, GROUPED>(e, ph, k, A, L)) continue;  // fatal at this element: the host stops at the first one in index order
-      const uint32_t col = coo_out_index<MODE>(e);
-      if (col != c) {
-        // the element no longer belongs to this output entry: leave it to the fix-up kernel
-        const uint32_t slot = atomicAdd(&A.stray[0], 1u);
-        if (slot < kMaxStray) A.stray[1 + slot] = GROUPED ? A.perm[k] : ph;
-        continue;
+    if (GROUPED) {
+      // the group is stored in place, in order: stream it, the next element's load in flight while this one is
+      // checked (a repair only ever rewrites the element in hand, never the one already fetched)
+      uint4 nxt = kb < ke ? A.elements[kb] : make_uint4(0, 0, 0, 0);
+      for (uint32_t k = kb; k < ke; k++) {
+        const uint4 e = nxt;
+        if (k + 1 < ke) nxt = A.elements[k + 1];
+        coo_accumulate<MODE, GROUPED>(e, k, k, c, A, vec, L, sum);
       }
-      if (e.y >= A.N) continue;  // vec[] would be read out of bounds (UB in the reference): dropped, as in the oracle
-      sum = __dadd_rn(sum, __dmul_rn(coo_value(e), vec[e.y]));
+    } else {
+      for (uint32_t k = kb; k < ke; k++) {
+        const uint32_t ph = A.perm[k];
+        coo_accumulate<MODE, GROUPED>(A.elements[ph], ph, k, c, A, vec, L, sum);
+      }
     }
     result[c] = sum;
   }
