@@ -7,6 +7,8 @@
 #   3 coo      COO spmv timings (tools/time_spmv.py --format coo)
 #   4 c5       bench.py --workload powerlaw at the size BASELINE names (N = 2^23, ~1.9e8 non-zeros), sec7 and constraints
 #   5 bench    the default bench line
+#   7 multi    (not in the default list; needs `gpurun --gpus N`) BASELINE configs[3] and [4] row-partitioned over every
+#              GPU count the box offers: poisson2d_blocks sec8, powerlaw sec7 / constraints at the named size
 #   6 ncu      (not in the default list) `ncu --set full` of one spmv launch per mode named in $NCU_MODES (default
 #              "secded crc32c") with the library named by $ABFT_CUDA_LIB, reports under gpurun_out/ for tools/ncu_summary.py;
 #              plus the launch list of a short bench run.  Only after the same commands have run clean without ncu.
@@ -48,6 +50,18 @@ for st in "${stages[@]}"; do
       done ;;
     bench)
       python bench.py > gpurun_out/session_bench.json 2> gpurun_out/session_bench.err; echo "bench: rc=$?"; cat gpurun_out/session_bench.json ;;
+    multi)
+      ngpu=$(python -c "import torch; print(torch.cuda.device_count())")
+      for n in 2 4 8; do
+        [ "$n" -le "$ngpu" ] || continue
+        for wl in "poisson2d_blocks sec8" "powerlaw sec7" "powerlaw constraints"; do
+          set -- $wl
+          python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) \
+              bench.py --gpus $n --workload $1 --mode $2 --steps 100 --warmup 10 --all-modes 0 \
+              > gpurun_out/session_multi_${1}_${2}_n$n.json 2> gpurun_out/session_multi_${1}_${2}_n$n.err
+          echo "$1 $2 x$n: rc=$?"; tail -1 gpurun_out/session_multi_${1}_${2}_n$n.json | cut -c1-400
+        done
+      done ;;
     ncu)
       for m in ${NCU_MODES:-secded crc32c}; do
         python tools/prof_spmv.py --mode $m --reps 3 > /dev/null 2>&1 || { echo "prof_spmv $m failed without ncu: skipped"; continue; }
