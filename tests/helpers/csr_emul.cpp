@@ -15,6 +15,7 @@ namespace {
 struct Emu {
   int mode = 0;
   uint32_t n_rows = 0, n_cols = 0, nnz = 0;
+  uint32_t row_offset = 0, nnz_offset = 0;  // a row partition: global index of local row 0 / local element 0
   std::vector<uint32_t> cols, rowptr;  // padded like abft_cuda_matrix_create pads the device arrays
   std::vector<double> vals;
   std::vector<Tile> tiles;
@@ -60,8 +61,8 @@ void spmv_inst(Emu *e, const double *vec, double *result) {
   A.n_rows = e->n_rows;
   A.nnz = e->nnz;
   A.n_cols = e->n_cols;
-  A.row_offset = 0;
-  A.nnz_offset = 0;
+  A.row_offset = e->row_offset;
+  A.nnz_offset = e->nnz_offset;
 #if ABFT_ROWS_ECC
   A.rows_ecc = e->rows_ecc ? 1u : 0u;
 #endif
@@ -87,10 +88,23 @@ int emu_crc_walk(void) { return ABFT_CRC_WALK; }
 int emu_last_refill(void) { return ABFT_SPMV_LASTREFILL; }
 
 // create_matrix as abft_cuda_matrix_create_part does it: row pointers and check bits by the device kernels
+// a row partition, as abft_cuda_matrix_create_part takes it: n_rows local rows starting at global row row_offset,
+// coo_rows / cols are GLOBAL indices, nnz_offset = global index of the partition's first element
+void *emu_create_part(int mode, const uint32_t *cols, const uint32_t *coo_rows, const double *vals, int N, int nnz,
+                      int N_global, int row_offset, int nnz_offset);
+
 void *emu_create(int mode, const uint32_t *cols, const uint32_t *coo_rows, const double *vals, int N, int nnz) {
+  return emu_create_part(mode, cols, coo_rows, vals, N, nnz, N, 0, 0);
+}
+
+void *emu_create_part(int mode, const uint32_t *cols, const uint32_t *coo_rows, const double *vals, int N, int nnz,
+                      int N_global, int row_offset, int nnz_offset) {
   Emu *e = new Emu();
   e->mode = mode;
-  e->n_rows = e->n_cols = (uint32_t)N;
+  e->n_rows = (uint32_t)N;
+  e->n_cols = (uint32_t)N_global;
+  e->row_offset = (uint32_t)row_offset;
+  e->nnz_offset = (uint32_t)nnz_offset;
   e->nnz = (uint32_t)nnz;
   const size_t nz = (size_t)std::max(nnz, 1);
   e->cols.assign(nz + 16, 0u);
@@ -101,7 +115,7 @@ void *emu_create(int mode, const uint32_t *cols, const uint32_t *coo_rows, const
   e->partials.assign(1 << 16, 0.0);
   e->smem = (unsigned char *)aligned_alloc(128, (std::max(SpmvCfg<true>::dyn_smem, SpmvCfg<false>::dyn_smem) + 127) / 128 * 128);
   fill_crc_tables();
-  emu::launch(2, kBlock, [&] { rowptr_kernel(coo_rows, (uint32_t)nnz, (uint32_t)N, 0u, e->rowptr.data()); });
+  emu::launch(2, kBlock, [&] { rowptr_kernel(coo_rows, (uint32_t)nnz, (uint32_t)N, (uint32_t)row_offset, e->rowptr.data()); });
   if (mode >= ABFT_MODE_SED && mode <= ABFT_MODE_SECDED && nnz > 0)
     emu::launch(2, kBlock, [&] { encode_elements_kernel(mode, e->cols.data(), e->vals.data(), (uint32_t)nnz); });
   else if (mode == ABFT_MODE_CRC32C && N > 0)

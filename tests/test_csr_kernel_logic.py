@@ -42,6 +42,8 @@ def _build(tmp, name, flags):
     f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
     L.emu_create.restype = C.c_void_p
     L.emu_create.argtypes = [C.c_int, u32p, u32p, f64p, C.c_int, C.c_int]
+    L.emu_create_part.restype = C.c_void_p
+    L.emu_create_part.argtypes = [C.c_int, u32p, u32p, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.emu_destroy.argtypes = [C.c_void_p]
     L.emu_set_tiles.argtypes = [C.c_void_p, u32p, C.c_int, C.c_int, C.c_int]
     for f, t in ((L.emu_cols, C.c_uint32), (L.emu_rowptr, C.c_uint32), (L.emu_values, C.c_double)):
@@ -75,14 +77,23 @@ def EMU_UNIFORM(tmp_path_factory):
 class EmuMatrix:
     """create_matrix + the tile plan, as abft_cuda_matrix_create_part does it."""
 
-    def __init__(self, L, pkg, mode, t, grid=3):
-        self.L, self.mode, self.N, self.nnz = L, mode, t.N, int(t.cols.shape[0])
-        self.h = L.emu_create(MODES.index(mode), np.ascontiguousarray(t.cols, dtype=np.uint32),
-                              np.ascontiguousarray(t.rows, dtype=np.uint32), np.ascontiguousarray(t.vals, dtype=np.float64),
-                              t.N, self.nnz)
+    def __init__(self, L, pkg, mode, t, grid=3, rows=None):
+        """rows=(r0, r1): only that block of rows, as one rank of a row partition holds it (global columns and indices)"""
+        if rows is None:
+            cols, coo_rows, vals, n_rows, row0, nnz0 = t.cols, t.rows, t.vals, t.N, 0, 0
+        else:
+            r0, r1 = rows
+            sel = (t.rows >= r0) & (t.rows < r1)
+            cols, coo_rows, vals = t.cols[sel], t.rows[sel], t.vals[sel]
+            n_rows, row0, nnz0 = r1 - r0, r0, int(np.count_nonzero(t.rows < r0))
+        self.L, self.mode, self.N, self.nnz = L, mode, n_rows, int(cols.shape[0])
+        self.h = L.emu_create_part(MODES.index(mode), np.ascontiguousarray(cols, dtype=np.uint32),
+                                   np.ascontiguousarray(coo_rows, dtype=np.uint32), np.ascontiguousarray(vals, dtype=np.float64),
+                                   n_rows, self.nnz, t.N, row0, nnz0)
         assert self.h
         lib = pkg.capi.load()
         rowptr = self.rowptr.copy()
+        t = type("Part", (), {"N": n_rows})           # (below: the local row count)
 
         def plan(tile_nnz):
             n = lib.abft_cuda_plan_tiles(rowptr.ctypes.data, t.N, tile_nnz, None, 0)
@@ -453,4 +464,42 @@ def test_last_refill_variant(tmp_path_factory, pkg, O, mode):
                     if fatal:
                         break
                     assert np.array_equal(em.cols, om.cols), (name, grid, index, bit)
+            em.close()
+
+
+@pytest.mark.parametrize("mode", ["constraints", "sec7", "secded", "crc32c"])
+def test_row_partitions_report_global_indices(EMU, pkg, O, mode):
+    """A matrix cut into row blocks (what each rank of a multi-GPU run holds: global columns, global element indices):
+    every block's result slice equals the whole matrix's, and faults carry GLOBAL row / element numbers, so that the
+    per-rank lists put end to end are the single-GPU list."""
+    rng = np.random.default_rng(51)
+    for name in ("p3d_12", "powerlaw", "long_rows"):
+        t = shapes(pkg.matgen)[name]()
+        vec = rng.standard_normal(t.N)
+        cuts = [0] + sorted(int(c) for c in rng.choice(np.arange(1, t.N), 2, replace=False)) + [t.N]
+        om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+        parts = [EmuMatrix(EMU, pkg, mode, t, rows=(cuts[k], cuts[k + 1])) for k in range(3)]
+        nnz0 = [int(np.count_nonzero(t.rows < cuts[k])) for k in range(4)]
+        faults = []
+        for trial in range(3):
+            index = int(rng.integers(0, t.nnz))
+            bit = int(rng.integers(0, 88)) if mode != "constraints" else int(rng.integers(64, 88))
+            k = max(j for j in range(3) if nnz0[j] <= index)
+            parts[k].flip(index - nnz0[k], bit)
+            om.flip(index, bit)
+            faults.append((index, bit))
+        y0, fatal0, ev0 = om.spmv(vec)
+        got_events, got_fatal, ys = [], False, []
+        for k, em in enumerate(parts):
+            y, fatal, events, _ = em.spmv(vec)
+            ys.append(y)
+            if not got_fatal:                      # (the host stops at the first fatal event in row order)
+                got_events += events
+                got_fatal = fatal
+        assert (got_fatal, got_events) == (fatal0, ev0), (name, faults, got_events, ev0)
+        if not fatal0:
+            y = np.concatenate(ys)
+            lens = np.bincount(t.rows, minlength=t.N)
+            assert np.array_equal(y[lens <= 32].view(np.uint64), y0[lens <= 32].view(np.uint64)), name
+        for em in parts:
             em.close()
