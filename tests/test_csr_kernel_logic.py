@@ -503,3 +503,58 @@ def test_row_partitions_report_global_indices(EMU, pkg, O, mode):
             assert np.array_equal(y[lens <= 32].view(np.uint64), y0[lens <= 32].view(np.uint64)), name
         for em in parts:
             em.close()
+
+
+def _from_lens(mg, lens, seed):
+    rng = np.random.default_rng(seed)
+    lens = np.asarray(lens, dtype=np.int64)
+    N = int(max(len(lens), lens.max() if len(lens) else 1, 1))
+    lens = np.concatenate([lens, np.zeros(N - len(lens), dtype=np.int64)])
+    rows = np.repeat(np.arange(N), lens)
+    cols = np.concatenate([np.sort(rng.choice(N, int(l), replace=False)) for l in lens if l > 0]) if lens.sum() else np.zeros(0)
+    return mg.Triplets(cols, rows, rng.standard_normal(rows.shape[0]), N)
+
+
+EDGE_LENS = {
+    "exactly_one_static_tile": [2048],            # one row as long as a static tile
+    "dyn_tile_boundary": [1536, 1537, 3],         # at and just past the dynamic tile size
+    "seq_threshold": [32, 33, 31, 0, 64],         # rows of 32 are summed sequentially, 33 by the warp
+    "mostly_empty": [0, 0, 5, 0, 0, 0, 0, 7, 0],
+    "trailing_empty": [3, 4] + [0] * 40,
+    "row_limit": [1] * 257 + [6] * 300,           # tiles capped by the 256-row limit, then by elements
+    "chunked_walk": [8, 9, 10, 11, 12] * 60,      # regular tiles whose rows are longer than the unrolled walks
+    "zigzag": [1, 63] * 50,                       # irregular
+    "no_elements": [0, 0, 0],
+    "odd_sizes": [5] * 259,                       # row / element counts that are not multiples of the 16-byte windows
+}
+
+
+@pytest.mark.parametrize("mode", ["none", "constraints", "secded", "crc32c"])
+def test_edge_shapes(EMU, pkg, O, mode):
+    rng = np.random.default_rng(61)
+    for name, lens in EDGE_LENS.items():
+        t = _from_lens(pkg.matgen, lens, 7)
+        em = EmuMatrix(EMU, pkg, mode, t)
+        om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+        assert np.array_equal(em.rowptr, om.rows) and np.array_equal(em.cols, om.cols), name
+        vec = rng.standard_normal(t.N)
+        y, fatal, events, dot = em.spmv(vec)
+        y0, _, _ = om.spmv(vec)
+        rl = np.bincount(t.rows, minlength=t.N)
+        scale = max(np.abs(t.vals).max() if t.nnz else 0.0, 1e-300) * np.abs(vec).max() * max(int(rl.max()), 1)
+        assert not fatal and events == [], (name, events)
+        assert np.array_equal(y[rl <= 32].view(np.uint64), y0[rl <= 32].view(np.uint64)), name
+        assert np.max(np.abs(y - y0)) <= 1e-13 * scale, name
+        assert abs(dot - float(np.dot(vec, y0))) <= 1e-10 * max(np.abs(vec * y0).sum(), 1e-300), name
+        if t.nnz and mode in ("secded", "crc32c"):
+            for index in {0, t.nnz - 1, t.nnz // 2}:
+                em.flip(index, 17)
+                om.flip(index, 17)
+                _, fatal, events, _ = em.spmv(vec)
+                _, fatal0, ev0 = om.spmv(vec)
+                assert (fatal, events) == (fatal0, ev0), (name, index)
+                em.cols[index], em.values[index] = om.cols[index], om.values[index]
+                if fatal0:          # (crc32c is detect-only: put the bit back on both sides)
+                    em.flip(index, 17)
+                    om.flip(index, 17)
+        em.close()
