@@ -15,6 +15,8 @@ VARIANTS=(
   "uni:-DABFT_WALK_UNIFORM=1"
   "uni_t1536:-DABFT_WALK_UNIFORM=1 -DABFT_TILE_STATIC=1536"
   "t1536:-DABFT_TILE_STATIC=1536"
+  "t1792:-DABFT_TILE_STATIC=1792"
+  "uni_t1792:-DABFT_WALK_UNIFORM=1 -DABFT_TILE_STATIC=1792"
   "uni_minb3:-DABFT_WALK_UNIFORM=1 -DABFT_SPMV_MINB=3"
   "crc5:-DABFT_CRC_CHUNK=5"
   "crc5_t1536:-DABFT_CRC_CHUNK=5 -DABFT_TILE_STATIC=1536"
