@@ -3,6 +3,7 @@
 #
 #   tools/ab_variants.sh build            # here (no GPU): nvcc cross-compiles into build/variants/ (travels with gpurun)
 #   tools/ab_variants.sh run [reps]       # on the GPU box: parity tests + spmv timings per variant -> gpurun_out/ab_variants.jsonl
+#                                         # (AB_ONLY="base uni ..." restricts the list; ~1.5 min of GPU per variant)
 #
 # Variants (name:flags).  `base` is the shipped configuration.  Knobs: spmv.cuh (ABFT_WALK_UNIFORM, ABFT_TILE_STATIC,
 # ABFT_TILE_DYN, ABFT_SPMV_MINB, ABFT_ELEM_BATCH, ABFT_CRC_CHUNK, ABFT_CRC_WALK, ABFT_SPMV_LASTREFILL; ABFT_ROWS_ECC in rowsecc.cuh).  A variant is only ever adopted after `run` shows it parity-green
@@ -46,6 +47,8 @@ case "${1:-}" in
     : > "$ROOT/gpurun_out/ab_variants.jsonl"
     for v in "${VARIANTS[@]}"; do
       name="${v%%:*}"
+      # AB_ONLY="base uni t1792": only these (default: all)
+      if [ -n "${AB_ONLY:-}" ] && ! [[ " $AB_ONLY " == *" $name "* ]]; then continue; fi
       lib="$OUT/libabftcuda_$name.so"
       [ -f "$lib" ] || { echo "missing $lib (run: tools/ab_variants.sh build)"; continue; }
       # parity first: a variant that is not bit-exact is not timed
