@@ -26,6 +26,7 @@ for st in "${stages[@]}"; do
           > gpurun_out/session_pytest_optin.txt 2>&1; echo "opt-in suites: rc=$?"
       tail -3 gpurun_out/session_pytest_gpu.txt gpurun_out/session_pytest_optin.txt ;;
     ab)
+      ls build/variants/libabftcuda_base.so > /dev/null 2>&1 || echo "build/variants is empty: run tools/ab_variants.sh build BEFORE gpurun (nvcc cross-compiles in the container)"
       tools/ab_variants.sh run 50 > gpurun_out/session_ab.txt 2>&1; echo "ab kit: rc=$?"; tail -40 gpurun_out/session_ab.txt ;;
     coo)
       # the opt-in grouped element layout (coo.cuh): parity first, then both layouts timed
