@@ -892,7 +892,11 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           const uint32_t *sc = B.cols + (rs - cb);
           const double *sv = B.vals + (rs - vb);
           uint32_t suspect = 0;
-          if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
+          // max_len is what create_matrix saw.  A corrupted rows[] can make this row longer while keeping it inside
+          // the window; the reference walks the whole [start, end) range (CSR/CPUContext.cpp:125,184), so such a
+          // row goes down the one-by-one path instead of an unrolled walk that would stop after max_len elements.
+          if (max_len <= 7 && len > (max_len <= 4 ? 4u : max_len)) suspect = 1u;
+          else if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
           else if (max_len == 5) sum = walk_chunk<MODE, 5>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
           else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
           else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
@@ -907,7 +911,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         if (MODE == ABFT_MODE_CRC32C) {
           const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the CTA
           const uint32_t len = re - rs;
-          if (max_len <= 7 && len >= 4) {
+          if (max_len <= 7 && len >= 4 && len <= (max_len <= 4 ? 4u : max_len)) {
             const uint32_t *sc = B.cols + (rs - cb);
             const double *sv = B.vals + (rs - vb);
             bool bad = false;
@@ -987,14 +991,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
       __syncthreads();  // everyone is done with stage `st`: it may be refilled
     }
   }
-  if (dynamic && tid == 0 && it > 0) {
-    // the last tile's dot() partial
-    const double *wd = s_wdot[(it - 1) & 1u];
-    double tp = wd[0];
-#pragma unroll
-    for (int k = 1; k < kBlock / 32; k++) tp = __dadd_rn(tp, wd[k]);
-    red.partials[s_tidx[(it - 1) % kStages]] = tp;
-  }
+  // (dynamic schedule: the loop only ends at the marker, whose iteration has already banked the last tile's partial)
   // fused dot(vec, result): CTA partials (static) or the per-tile partials (dynamic), then the grid-wide deterministic sum
   const double mine = dynamic ? 0.0 : block_sum(dot_part, s_warp);
   const bool last = grid_sum_finalize(mine, red, s_warp, dynamic ? A.n_tiles : 0u);

@@ -1,9 +1,5 @@
 """The COO drop-in: the reference's UNMODIFIED cg.cpp driver linked with host/COOCUDAContext.cpp, run as
 `cg-coo -t cuda`, against the same binary's `-t cpu` and against the reference cg-coo CLI fixtures.
-
-OPT-IN (ABFT_COO_CLI_TESTS=1): the C ABI underneath is parity green on a B200 (tests/test_gpu_coo.py), but this
-binary was built after round 1's GPU budget was spent and has not been driven on a GPU yet -- so it does not ride
-along with `pytest -m gpu` until it has been seen green once.
 """
 import os
 
@@ -11,9 +7,7 @@ import pytest
 
 from conftest import load_golden
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ABFT_COO_CLI_TESTS") != "1",
-                                 reason="cg-coo-cuda not yet driven on a GPU (set ABFT_COO_CLI_TESTS=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "oracle", "_ref", "cg-coo-cuda")

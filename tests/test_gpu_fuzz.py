@@ -4,8 +4,6 @@ on the device and through the CPU oracle -- which the CPU suite runs against the
 distribution (tests/test_oracle_ref.py).  Same events in the same order, same fatal verdict, same repaired matrix,
 same result[] (bit for bit where the kernels keep the sequential order: rows of up to 32 elements; the oracle and the
 kernels clamp out-of-range columns alike, so nothing is skipped here).
-
-Opt-in (ABFT_GPU_FUZZ=1) until it has been seen green on a B200: written in a session without GPU time left.
 """
 import importlib.util
 import os
@@ -13,8 +11,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ABFT_GPU_FUZZ") != "1", reason="opt-in: ABFT_GPU_FUZZ=1 (not yet run on hardware)")]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 

@@ -498,6 +498,30 @@ def test_constraints_row_pointer_faults(pkg, O):
         ctx.close()
 
 
+@pytest.mark.parametrize("mode", ["none", "constraints", "secded", "crc32c"])
+def test_row_pointer_fault_that_lengthens_a_row_inside_its_tile(pkg, O, mode):
+    """A corrupted rows[] entry that makes a row LONGER than the tile's build-time longest row while the columns stay
+    increasing across the old row boundary: the reference walks the whole [start, end) range
+    (CSR/CPUContext.cpp:125,184), so must the unrolled fast walk (it used to stop after max_len elements)."""
+    N = 64
+    idx = np.arange(N, dtype=np.uint32)
+    for t, row, value in [(pkg.matgen.Triplets(idx, idx, np.arange(1.0, N + 1), N), 11, 17),       # diagonal: 1 -> 7 long
+                          (pkg.matgen.poisson2d(12), 31, 31 * 5 - 2 + 9)]:
+        vec = pkg.matgen.rhs(t.N)
+        ctx, A, om = make(pkg, O, mode, t)
+        if mode == "crc32c" and t.N == N:
+            ctx.close()
+            continue   # 1-element rows carry per-element SECDED bytes: lengthening one is a CRC/ECC fault of its own
+        ctx._ck(ctx.L.abft_cuda_matrix_poke_rowptr(ctx.ctx, A.handle, row, value), "poke")
+        om.rows[row] = value
+        y, fatal, events, _ = gpu_spmv(ctx, A, vec)
+        y0, fatal0, ev0 = om.spmv(vec)
+        assert (fatal, events) == (fatal0, ev0), (mode, row, value)
+        if not fatal:
+            assert np.array_equal(y.view(np.uint64), y0.view(np.uint64)), (mode, row, value)
+        ctx.close()
+
+
 def test_multiple_faults_are_reported_in_serial_order(pkg, O):
     """Several corrupted elements: events come back sorted like the serial CPU loop visits them,
     and everything after the first fatal one is dropped (the reference has exit(1)ed)."""
