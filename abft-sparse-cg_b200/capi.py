@@ -13,16 +13,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ABFT_CUDA_LIB") or os.path.join(HERE, "libabftcuda.so")   # override: kernel experiments
 
 MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"]
-FATAL_KINDS = {1, 4, 5, 6, 7, 8, 9}
+FATAL_KINDS = {1, 4, 5, 6, 7, 8, 9, 11, 12}
 
 # every extern "C" symbol include/abft_cuda.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "abft_cuda_abi_version", "abft_cuda_last_error", "abft_cuda_mode_name", "abft_cuda_mode_from_name",
     "abft_cuda_device_count", "abft_cuda_format_event", "abft_cuda_event_is_fatal",
     "abft_cuda_ctx_create", "abft_cuda_ctx_destroy", "abft_cuda_ctx_mode", "abft_cuda_ctx_sync",
-    "abft_cuda_ctx_stream",
+    "abft_cuda_ctx_stream", "abft_cuda_phases_enable", "abft_cuda_phases_read",
     "abft_cuda_matrix_create", "abft_cuda_matrix_create_part", "abft_cuda_matrix_destroy",
-    "abft_cuda_plan_tiles", "abft_cuda_matrix_rows", "abft_cuda_matrix_nnz", "abft_cuda_matrix_read", "abft_cuda_matrix_poke_rowptr",
+    "abft_cuda_plan_tiles", "abft_cuda_plan_matrix", "abft_cuda_matrix_rows", "abft_cuda_matrix_nnz", "abft_cuda_matrix_read", "abft_cuda_matrix_poke_rowptr",
     "abft_cuda_matrix_poke_col", "abft_cuda_matrix_poke_value",
     "abft_cuda_vector_create", "abft_cuda_vector_wrap", "abft_cuda_vector_view", "abft_cuda_vector_destroy",
     "abft_cuda_vector_len", "abft_cuda_vector_dev_ptr", "abft_cuda_vector_map", "abft_cuda_vector_unmap",
@@ -30,7 +30,7 @@ SYMBOLS = [
     "abft_cuda_spmv", "abft_cuda_dot", "abft_cuda_calc_xr", "abft_cuda_calc_p",
     "abft_cuda_dot_async", "abft_cuda_calc_xr_async", "abft_cuda_scalar_dev_ptr", "abft_cuda_scalar_host",
     "abft_cuda_flip_bit", "abft_cuda_poll_events", "abft_cuda_events_pending",
-    "abft_cuda_cg_solve", "abft_cuda_launch_count", "abft_cuda_matrix_tiles",
+    "abft_cuda_cg_solve", "abft_cuda_cg_host_loop", "abft_cuda_dist_cg_host_loop", "abft_cuda_launch_count", "abft_cuda_matrix_tiles",
     "abft_cuda_comm_create", "abft_cuda_comm_destroy", "abft_cuda_comm_window_handle", "abft_cuda_vector_ipc_handle",
     "abft_cuda_comm_window_ptr", "abft_cuda_comm_attach_self", "abft_cuda_comm_attach_peer",
     "abft_cuda_comm_attach_peer_ptrs", "abft_cuda_comm_set_plan", "abft_cuda_dist_push", "abft_cuda_dist_calc_p",
@@ -82,10 +82,13 @@ def load():
     sig("abft_cuda_ctx_mode", i32, vp)
     sig("abft_cuda_ctx_sync", i32, vp)
     sig("abft_cuda_ctx_stream", vp, vp)
+    sig("abft_cuda_phases_enable", i32, vp, i32)
+    sig("abft_cuda_phases_read", i32, vp, vp, i32)
     sig("abft_cuda_matrix_create", vp, vp, vp, vp, vp, i32, i32)
     sig("abft_cuda_matrix_create_part", vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_int64)
     sig("abft_cuda_matrix_destroy", None, vp, vp)
     sig("abft_cuda_plan_tiles", i32, vp, i32, i32, vp, i32)
+    sig("abft_cuda_plan_matrix", i32, vp, i32, i32, vp, i32, C.POINTER(C.c_int))
     sig("abft_cuda_matrix_rows", i32, vp)
     sig("abft_cuda_matrix_nnz", i32, vp)
     sig("abft_cuda_matrix_tiles", i32, vp)
@@ -114,6 +117,8 @@ def load():
     sig("abft_cuda_poll_events", i32, vp, C.POINTER(Event), i32, C.POINTER(C.c_int))
     sig("abft_cuda_events_pending", i32, vp)
     sig("abft_cuda_cg_solve", i32, vp, vp, vp, vp, vp, vp, vp, i32, f64, i32, f64p)
+    sig("abft_cuda_cg_host_loop", i32, vp, vp, vp, vp, vp, vp, i32, f64, f64p, vp)
+    sig("abft_cuda_dist_cg_host_loop", i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, f64p, vp)
     sig("abft_cuda_launch_count", C.c_uint64, vp)
     i32p = C.POINTER(C.c_int)
     sig("abft_cuda_comm_create", vp, vp, i32, i32)

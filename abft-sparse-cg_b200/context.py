@@ -185,12 +185,18 @@ class CUDAContext:
 
     # ---- fault reporting ----
     def poll_events(self, cap=256):
+        """Every queued event in the reference's serial order (the library hands them out `cap` at a time), and
+        whether the last one is fatal."""
         buf = (capi.Event * cap)()
         fatal = C.c_int(0)
-        n = self.L.abft_cuda_poll_events(self.ctx, buf, cap, C.byref(fatal))
-        if n < 0:
-            raise RuntimeError("cuda target: poll_events failed: " + capi.last_error())
-        return [(buf[i].kind, buf[i].index, buf[i].bit) for i in range(n)], bool(fatal.value)
+        out = []
+        while True:
+            n = self.L.abft_cuda_poll_events(self.ctx, buf, cap, C.byref(fatal))
+            if n < 0:
+                raise RuntimeError("cuda target: poll_events failed: " + capi.last_error())
+            out += [(buf[i].kind, buf[i].index, buf[i].bit) for i in range(n)]
+            if n == 0 or fatal.value:
+                return out, bool(fatal.value)
 
     def format_event(self, ev) -> str:
         e = capi.Event(*ev)
@@ -228,6 +234,27 @@ class CUDAContext:
             hist.append(rr)
             itr += 1
         return itr, np.asarray(hist)
+
+    def cg_host_loop(self, A, x, r, p, w, max_itrs, conv_threshold, rr, hist=None):
+        """abft_cuda_cg_host_loop: the loop body of cg() above, compiled (same four entry points, same order) ->
+        (iterations, rr).  Raises FatalFault where the reference would exit(1); a repaired fault is reported and the
+        loop goes on."""
+        rr_io = C.c_double(rr)
+        done = 0
+        while done < max_itrs and rr_io.value > conv_threshold:
+            buf = np.zeros(max(max_itrs - done, 1)) if hist is not None else None
+            n = self.L.abft_cuda_cg_host_loop(self.ctx, A.handle, x.handle, r.handle, p.handle, w.handle, int(max_itrs - done),
+                                              float(conv_threshold), C.byref(rr_io), _ptr(buf) if buf is not None else None)
+            if n < 0:
+                raise RuntimeError("cuda target: cg_host_loop failed: " + capi.last_error())
+            if hist is not None:
+                hist.extend(buf[:n].tolist())
+            done += n
+            if self.L.abft_cuda_events_pending(self.ctx):
+                self.report_faults()
+            elif n == 0:
+                break
+        return done, rr_io.value
 
     # ---- COO format (the reference's cg-coo; COO/CPUContext.cpp) ----
     COO_ELEM = np.dtype([("col", np.uint32), ("row", np.uint32), ("value", np.float64)])

@@ -9,7 +9,7 @@
 namespace abft {
 
 constexpr int kBlock = 256;            // threads per CTA of every kernel here
-constexpr int kLogCap = 2048;          // device-side fault records kept between polls
+constexpr int kLogCap = 16384;         // device-side fault records kept between polls (more: ABFT_EV_LOG_OVERFLOW)
 constexpr int kNumSlots = 8;           // scalar result slots
 constexpr int kMaxPartials = 1 << 20;  // per-CTA partial sums of one reduction
 
@@ -33,6 +33,34 @@ __device__ __forceinline__ void log_event(const LogRef &L, int kind, uint32_t in
     L.log->ev[slot].bit = bit;
   }
   *L.flag = 1u;
+  __threadfence_system();  // (rare path) the host may learn of the kernel's end by polling a word, not by a stream sync
+}
+
+// ---- phase stamps (off unless abft_cuda_phases_enable was called: the pointer is null) --------------------------------
+// Where a partitioned CG iteration spends its time besides the streams: one 64-bit globaltimer value (ns, one clock for
+// all GPUs of a box) per event, written by a single thread.  A row of kPhaseSlots stamps per iteration:
+enum {
+  PH_SPMV_BEGIN = 0,      // spmv: CTA 0 starts
+  PH_SPMV_WAIT_END = 1,   // spmv: CTA 0 has seen every peer's push of p (== PH_SPMV_BEGIN + wait)
+  PH_SPMV_REDUCE = 2,     // spmv: the last CTA enters the cross-rank all-reduce of p.w (its own rows are done)
+  PH_SPMV_END = 3,        // spmv: all ranks' partials are in, p.w published
+  PH_XR_BEGIN = 4,        // calc_xr: CTA 0 starts (after the host round trip on the plugin path)
+  PH_XR_REDUCE = 5,       // calc_xr: the last CTA enters the all-reduce of r.r
+  PH_XR_END = 6,          // calc_xr: r.r published
+  PH_P_BEGIN = 7,         // calc_p (+ push): CTA 0 starts
+  PH_P_END = 8,           // calc_p: every store to the peers has landed, flags raised
+  kPhaseSlots = 12
+};
+__device__ __forceinline__ void phase_stamp(unsigned long long *row, int slot) {
+#ifndef ABFT_HOST_EMU
+  if (row) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    row[slot] = t;
+  }
+#else
+  (void)row; (void)slot;
+#endif
 }
 
 // ---- loads -------------------------------------------------------------------
@@ -50,17 +78,18 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// all threads of the CTA must call; result valid in thread 0
-__device__ __forceinline__ double block_sum(double v, double *s_warp /* [kBlock/32] */) {
+// all threads of the CTA (BLOCK of them) must call; result valid in thread 0
+template <int BLOCK = kBlock>
+__device__ __forceinline__ double block_sum(double v, double *s_warp /* [BLOCK/32] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v = warp_sum(v);
   if (lane == 0) s_warp[warp] = v;
   __syncthreads();
   double t = 0.0;
   if (warp == 0) {
-    t = (lane < kBlock / 32) ? s_warp[lane] : 0.0;
+    t = (lane < BLOCK / 32) ? s_warp[lane] : 0.0;
 #pragma unroll
-    for (int o = (kBlock / 64); o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    for (int o = (BLOCK / 64); o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
   }
   __syncthreads();
   return t;
@@ -72,18 +101,17 @@ __device__ __forceinline__ double block_sum(double v, double *s_warp /* [kBlock/
 constexpr int kMaxRanks = 8;
 
 struct CommWindow {
-  double slots[2][kMaxRanks];      // [parity of the reduction sequence number][source rank]
-  unsigned int rflag[kMaxRanks];   // last reduction sequence number published by each source rank
+  double slots[2][kMaxRanks];      // [parity of the reduction sequence number][source rank]; kSlotEmpty when consumed
   unsigned int pflag[kMaxRanks];   // last vector-push epoch completed by each source rank
   unsigned int push_counter;       // local: CTAs of the running push kernel that are done
-  unsigned int pad[15];
+  unsigned int pad[23];
 };
 
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
   return *reinterpret_cast<const volatile unsigned int *>(p);
 }
-__device__ __forceinline__ double ld_volatile_f64(const double *p) {
-  return *reinterpret_cast<const volatile double *>(p);
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const double *p) {
+  return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
 
 // Cross-rank part of a reduction: all-reduce (sum, fixed rank order => every rank gets the same
@@ -95,21 +123,31 @@ struct PeerReduce {
   unsigned int seq;            // this reduction's sequence number (same on every rank)
 };
 
-// called by ONE thread; returns the global sum
-__device__ __forceinline__ double peer_allreduce(double mine, const PeerReduce &pr) {
+// A slot that holds no contribution: a NaN bit pattern no computation produces (a partial that happens to be this
+// very NaN is sent as another NaN).  The data word is its own arrival flag: one 8-byte store per peer, no fence and
+// no second round of flag stores on the critical path (round 1 stored data, fenced system-wide, then stored flags).
+constexpr unsigned long long kSlotEmpty = 0x7FF8ABF7C0DE5EEDull;
+
+// Called by the first `world` lanes of ONE warp together (lane s talks to rank s); every calling lane returns the
+// global sum.  Rank r stores its partial into slot [seq & 1][r] of every rank's window (its own included), each lane
+// spins on its own slot of the local window, the partials are added in rank order, and the lane empties the slot it
+// has read.  A rank can run at most one reduction ahead of the slowest rank (it needs everybody's partial to finish),
+// and then it writes the other parity; the slot it will write two reductions later was emptied before its owner
+// sent the partial of the reduction in between (program order + the kernel boundary between two reductions).
+__device__ __forceinline__ double peer_allreduce(double mine, const PeerReduce &pr, int lane) {
   const int par = (int)(pr.seq & 1u);
-  for (int s = 0; s < pr.world; s++) pr.win[s]->slots[par][pr.rank] = mine;
-  __threadfence_system();
-  for (int s = 0; s < pr.world; s++) *reinterpret_cast<volatile unsigned int *>(&pr.win[s]->rflag[pr.rank]) = pr.seq;
-  const CommWindow *me = pr.win[pr.rank];
-  double total = 0.0;
-  for (int s = 0; s < pr.world; s++) {
-    // a rank can run at most one reduction ahead, and then it writes the other parity
-    while ((int)(ld_volatile_u32(&me->rflag[s]) - pr.seq) < 0) {
-    }
+  unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+  if (bits == kSlotEmpty) bits ^= 1ull;
+  const unsigned int peers = (1u << pr.world) - 1u;
+  *reinterpret_cast<volatile unsigned long long *>(&pr.win[lane]->slots[par][pr.rank]) = bits;
+  double *slot = &pr.win[pr.rank]->slots[par][lane];
+  unsigned long long got;
+  while ((got = ld_volatile_u64(slot)) == kSlotEmpty) {
   }
-  __threadfence_system();
-  for (int s = 0; s < pr.world; s++) total += ld_volatile_f64(&me->slots[par][s]);
+  *reinterpret_cast<volatile unsigned long long *>(slot) = kSlotEmpty;
+  const double v = __longlong_as_double((long long)got);
+  double total = 0.0;
+  for (int s = 0; s < pr.world; s++) total += __shfl_sync(peers, v, s);
   return total;
 }
 
@@ -120,6 +158,8 @@ struct ReduceOut {
   unsigned int *counter;   // zero before launch; reset by the last CTA
   double *dev;             // device scalar slot
   volatile double *host;   // mapped pinned copy of the slot
+  volatile unsigned int *host_seq;  // mapped pinned: set to seq_value once *host is written (null: not wanted)
+  unsigned int seq_value;
   // device-resident loop control (null when driven from the host)
   int *active;             // set to (value > threshold && *iters < max_itrs) by the finalizer
   int *iters;
@@ -127,12 +167,15 @@ struct ReduceOut {
   int max_itrs;
   int bump_iters;          // 1: this reduction closes an iteration (calc_xr)
   PeerReduce peers;        // world > 1: the value published is the sum over all ranks
+  unsigned long long *phase;  // this iteration's row of phase stamps (null: off)
+  int phase_slot;             // PH_SPMV_REDUCE or PH_XR_REDUCE: the stamp taken on entering the all-reduce (+1 on leaving)
 };
 
 // Every CTA contributes `mine` (valid in thread 0); the CTA that arrives last
 // adds the partials in index order with a fixed tree and publishes the value.
 // n_given != 0: the CTAs have already stored o.partials[0 .. n_given) themselves (spmv's per-tile partials) and
 // `mine` is ignored.  Returns true in every thread of the CTA that did the final sum.
+template <int BLOCK = kBlock>
 __device__ __forceinline__ bool grid_sum_finalize(double mine, const ReduceOut &o, double *s_warp, unsigned int n_given = 0) {
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
@@ -146,10 +189,18 @@ __device__ __forceinline__ bool grid_sum_finalize(double mine, const ReduceOut &
   __threadfence();
   double acc = 0.0;
   const unsigned int n_partials = n_given ? n_given : gridDim.x;
-  for (unsigned int i = threadIdx.x; i < n_partials; i += kBlock) acc += __ldcg(o.partials + i);
-  double total = block_sum(acc, s_warp);
+  for (unsigned int i = threadIdx.x; i < n_partials; i += BLOCK) acc += __ldcg(o.partials + i);
+  double total = block_sum<BLOCK>(acc, s_warp);
+  if (threadIdx.x == 0) phase_stamp(o.phase, o.phase_slot);
+  if (o.peers.world > 1) {
+    // the first `world` lanes of warp 0 exchange the partials with the peers (lane s <-> rank s)
+    if (threadIdx.x < 32) {
+      total = __shfl_sync(0xffffffffu, total, 0);
+      if ((int)threadIdx.x < o.peers.world) total = peer_allreduce(total, o.peers, (int)threadIdx.x);
+    }
+  }
   if (threadIdx.x == 0) {
-    if (o.peers.world > 1) total = peer_allreduce(total, o.peers);
+    phase_stamp(o.phase, o.phase_slot + 1);
     *o.dev = total;
     if (o.host) *o.host = total;
     if (o.active) {
@@ -158,6 +209,11 @@ __device__ __forceinline__ bool grid_sum_finalize(double mine, const ReduceOut &
       *o.active = (total > o.threshold && it < o.max_itrs) ? 1 : 0;
     }
     *o.counter = 0u;
+    if (o.host_seq) {
+      // the host polls this word instead of synchronising the stream: value first, then its sequence number
+      __threadfence_system();
+      *o.host_seq = o.seq_value;
+    }
     __threadfence_system();
   }
   return true;

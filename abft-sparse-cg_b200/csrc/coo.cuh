@@ -2,8 +2,9 @@
 // {col, row, value} with the check byte in col bits 24..31 (reference: COO/ecc.h:7-16, COO/CPUContext.cpp).
 //
 // STATUS: parity green on a B200 against oracle/coo_oracle.c, which is pinned against the reference
-// (tests/test_gpu_coo.py: encoded elements, result[], events, repaired elements bit for bit; CG iteration counts).
-// Correctness first: no TMA staging, no fused dot, not yet profiled or tuned (DESIGN.md 0, row f).
+// (tests/test_gpu_coo.py: encoded elements, result[], events, repaired elements bit for bit; CG iteration counts), in
+// both element layouts; measured on 256^3 (profiles/r2_coo_layouts.jsonl): grouped layout 0.40 ms none / 0.46 ms secded
+// = 0.81 / 0.72 of the format's own roofline (16 B per element + the two vectors), caller-order layout 0.53 / 0.60 ms.
 //
 // The reference's loop is a scatter: for every element in index order, result[col] += value * vec[row]
 // (COO/CPUContext.cpp:104-121).  Each output entry therefore accumulates its elements in ascending element
@@ -19,8 +20,8 @@
 // Result: the reference's result[] in every case the reference defines (it reads/writes out of bounds when
 // an index leaves [0, N): such an element is dropped here and in the oracle).
 //
-// GROUPED layout (opt-in at create_matrix, ABFT_CUDA_COO_LAYOUT=grouped; logic checked on the CPU, not yet run or timed
-// on a GPU): the elements are STORED in group order -- slot k of `perm` -- so thread c streams its group with
+// GROUPED layout (the default; ABFT_CUDA_COO_LAYOUT=caller at create_matrix keeps the elements where the caller put
+// them): the elements are STORED in group order -- slot k of `perm` -- so thread c streams its group with
 // consecutive 128-bit loads instead of gathering 16-byte elements through `perm` (which is then only read to name an
 // element in a fault record); `pos` (element index -> slot) serves inject_bitflip, the CONSTRAINTS neighbour and the
 // stray fix-up.  Everything observable keeps the caller's numbering: fault indices, abft_cuda_coo_matrix_read.
@@ -250,8 +251,11 @@ coo_spmv_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ 
 // group (minus the members that strayed away) and the strays that target it, in ascending element index.
 // The elements were already checked / repaired by coo_spmv_kernel; nothing is logged here.
 template <int MODE, bool GROUPED>
-__global__ void coo_stray_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ result) {
+__global__ void coo_stray_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ result, LogRef L) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // more index faults in one spmv than the list holds: the products of the ones that did not fit are lost, so
+  // result[] is wrong -- said out loud (fatal), not silently (bit = 1 tells the host which list overflowed)
+  if (A.stray[0] > kMaxStray) log_event(L, ABFT_EV_LOG_OVERFLOW, A.stray[0] - kMaxStray, 1u);
   const uint32_t n = min(A.stray[0], kMaxStray);
   A.stray[0] = 0;
   for (uint32_t s = 0; s < n; s++) {

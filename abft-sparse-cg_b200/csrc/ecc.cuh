@@ -117,4 +117,14 @@ constexpr uint32_t crc32c_table_entry(uint32_t i, int slice) {
   return c;
 }
 
+// The spmv check's tables (spmv.cuh, "CRC32C row check"): F = "advance the raw state over four zero bytes" is linear,
+// so F^m(x) is the XOR of one table entry per 5-bit chunk of x.  Entry c of the table of chunk j of map F^m (m = 1..3):
+constexpr int kCrcMaps = 3, kCrcChunks = 7;
+constexpr int kCrcTabWords = kCrcMaps * kCrcChunks * 32;
+constexpr uint32_t crc5_entry(int m, int j, uint32_t c) {   // (host side: library init)
+  uint32_t x = (uint32_t)((uint64_t)c << (5 * j));
+  for (int r = 0; r < 4 * m; r++) x = (x >> 8) ^ crc32c_table_entry(x & 0xFFu, 0);
+  return x;
+}
+
 }  // namespace abft

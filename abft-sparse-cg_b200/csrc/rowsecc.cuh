@@ -3,8 +3,8 @@
 // NOT IN THE REFERENCE: its modes protect cols[] / values[] only and trust rows[] (CSR/CPUContext.cpp:123-124; only
 // `constraints` looks at it).  This is this repository's own definition, in the style of the element codes of
 // CSR/ecc.h, and -- like crc32c -- "parity unpinned": checked against oracle/rowptr_ecc.c only.
-// OPT-IN AT COMPILE TIME (-DABFT_ROWS_ECC=1) until it has run on a GPU: written in a session without GPU time; its
-// logic runs on the CPU emulator (tests/test_csr_kernel_logic.py).  Enabled per matrix with ABFT_CUDA_PROTECT_ROWS=secded.
+// Enabled per matrix with ABFT_CUDA_PROTECT_ROWS=secded at create_matrix (tests/test_gpu_rowptr.py on the device,
+// tests/test_rowptr_ecc.py on the CPU emulator).
 //
 // Code word = one PAIR of row pointers {rows[2k], rows[2k+1]}: 56 data bits (bits 0..27 of either word: nnz < 2^28) in
 // the non-power-of-two Hamming positions 3..62, six Hamming parities P1..P6 (position 2^(p-1)) in word0 bits 28..31 and
@@ -17,10 +17,6 @@
 // modes' own logic only ever sees clean pointers; the host reports row-pointer events ahead of element events.
 #pragma once
 #include <stdint.h>
-
-#ifndef ABFT_ROWS_ECC
-#define ABFT_ROWS_ECC 0
-#endif
 
 namespace abft {
 

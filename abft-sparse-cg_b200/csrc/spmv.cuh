@@ -5,7 +5,7 @@
 //
 // B200 design (DESIGN.md "spmv kernel"):
 //  * Work unit = "tile": a run of whole rows with <= kTileNnz non-zeros and
-//    <= kTileRows rows, built once in create_matrix.
+//    <= BLOCK rows (one per thread of the CTA), built once in create_matrix.
 //  * Persistent CTAs (grid = SMs x resident CTAs), tile t of CTA b is b + t*grid so
 //    the whole chip sweeps the matrix front together and vec[] stays L2-resident.
 //  * The tile's cols / values / row pointers are contiguous in memory: one elected
@@ -38,27 +38,26 @@
 
 namespace abft {
 
-#ifndef ABFT_TILE_STATIC
-#define ABFT_TILE_STATIC 2048
-#endif
-constexpr int kTileNnz = ABFT_TILE_STATIC;  // (knob for experiments; 2048 is what round 1 measured)
+// Threads per CTA = rows per tile (one row per thread on regular tiles); a tile holds up to 8 elements per row.
+// Measured on 256^3 secded (profiles/r2_ab_session2_block_sizes.jsonl, r2_ab_session3_warp_vs_cta.jsonl): 256 threads /
+// 2048-element tiles 0.33 ms; 128 threads 0.35; 64 threads 0.39; 512 threads 0.40; a private two-stage TMA ring per
+// warp (32-row tiles, no CTA barrier at all) 0.40 -- the per-tile bookkeeping (~100 instructions per warp per tile,
+// a quarter of everything executed) and the stream set-up grow faster than the barrier wait shrinks.
+constexpr int kSpmvBlock = kBlock;
+constexpr int kTileNnz = 8 * kSpmvBlock;
 // Matrices with irregular tiles (dynamic schedule) are gather-bound, and a gather in flight holds an L1 line: with
 // 4 CTAs x 52 KB of stage buffers the SM's 256 KB are all shared memory and the ~28 KB of L1 left cap the gathers in
 // flight (measured: same kernel, carveout forced down to 164 KB / 3 CTAs: 0.41 -> 0.32 ms).  Their tiles are smaller,
 // so that 4 CTAs need 160 KB and the L1 keeps 92 KB.  Measured on the power-law workload (sec7, 4 CTAs per SM):
 // 2048 -> 0.40 ms (L1 28 KB), 1536 -> 0.295 (92 KB), 1024 -> 0.335 (124 KB), 768 -> 0.378 (156 KB).
-#ifndef ABFT_TILE_DYN
-#define ABFT_TILE_DYN 1536
-#endif
-constexpr int kTileNnzDyn = ABFT_TILE_DYN;
-constexpr int kTileRows = kBlock;  // 256: one row per thread
+constexpr int kSpmvBlockDyn = kBlock;
+constexpr int kTileNnzDyn = 1536;
 constexpr int kStages = 2;
 constexpr uint32_t kSeqRowMax = 32;  // irregular tiles: rows up to this long are summed sequentially by one thread
-#ifndef ABFT_ELEM_BATCH
-#define ABFT_ELEM_BATCH 1  // measured on the power-law workload: 1 -> 0.50 ms, 2 -> 0.52, 4 -> 0.53, 8 -> 0.60 (gather-rate bound)
-#endif
 constexpr int kLongBatch = 4;  // rows longer than a tile: elements each thread streams at a time
-constexpr int kElemBatch = ABFT_ELEM_BATCH;          // irregular tiles: gathers each thread keeps in flight in the element phase
+// irregular tiles: gathers each thread keeps in flight in the element phase (measured on the power-law workload:
+// 1 -> 0.50 ms, 2 -> 0.52, 4 -> 0.53, 8 -> 0.60: the gather rate is the bound, not the loads in flight)
+constexpr int kElemBatch = 1;
 constexpr uint32_t kOverrun = 8;  // elements staged past a tile's end (>= longest unrolled walk - 1)
 
 constexpr uint32_t kTileNone = 0xFFFFFFFFu;   // info of the "no more tiles" marker
@@ -84,24 +83,23 @@ struct MatView {
   uint32_t n_cols;      // global N: bound for the gather
   uint32_t row_offset;  // global index of local row 0
   uint32_t nnz_offset;  // global index of local element 0 (for reported indices)
-#if ABFT_ROWS_ECC
   uint32_t rows_ecc;    // rowptr[] carries the SECDED pair code of rowsecc.cuh (check bits in bits 28..31)
-#endif
 };
 
 // one pipeline stage of staged tile data (windows start at 16-byte aligned indices)
 // (+16: the windows are rounded out to 16 bytes, and the unrolled row walk may read up to 6 slots
 // past a row's end)
-template <int TN>
+template <int TN, int ROWS>
 struct __align__(16) StageBufT {
   double vals[TN + 16];
   uint32_t cols[TN + 16];
-  uint32_t rptr[kTileRows + 8];
+  uint32_t rptr[ROWS + 8];
 };
 template <bool DYN>
 struct SpmvCfg {
+  static constexpr int block = DYN ? kSpmvBlockDyn : kSpmvBlock;   // threads per CTA = rows per tile
   static constexpr int tile_nnz = DYN ? kTileNnzDyn : kTileNnz;
-  using Stage = StageBufT<tile_nnz>;
+  using Stage = StageBufT<tile_nnz, block>;
   static constexpr size_t dyn_smem = sizeof(Stage) * kStages;
 };
 
@@ -301,6 +299,9 @@ __device__ __forceinline__ void batch_products(const uint32_t (&li)[U], const ui
 // zeroed and the matrix arrays end in zero padding), i.e. valid code words; at worst a faulty neighbour
 // raises a false `suspect` and sends this row down the (exact) careful path -- but they are never added.
 // That keeps the loop body free of selects and zero-fills.
+// `full`: a warp-uniform vote of the caller that every row of the warp fills the chunk (interior rows of a stencil:
+// 3 of 4 warps of a 256^3 tile); the adds then need no predicate (the predicated form costs an ISETP and two FSEL per
+// element: 280 instead of 320 instructions per 7-element SECDED row, measured 0.332 -> 0.325 ms on 256^3).
 template <int MODE, int LEN>
 __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_t count, const uint32_t *s_cols,
                                              const double *s_vals, uint32_t n_cols, const double *__restrict__ x,
@@ -314,6 +315,18 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
     v[k] = s_vals[first + k];
   }
   if (MODE == ABFT_MODE_CONSTRAINTS) c[LEN] = s_cols[first + LEN];
+  // every gather is issued before the first check: the ~35 instructions of one element's check do not cover an L2
+  // round trip, the ~250 of a whole row's do (ncu: 7 % of the stall samples sat on the first DMUL, waiting for the
+  // gather that had been issued last)
+#pragma unroll
+  for (int k = 0; k < LEN; k++) {
+    const uint32_t col = ModeTraits<MODE>::masks_column ? (c[k] & 0x00FFFFFFu) : c[k];
+    // A column no check caught (mode none, or a multi-bit fault the code cannot see) can point outside
+    // vec[]: the reference reads out of bounds there (UB); here, and in the oracle, the column is clamped
+    // to the last entry.
+    xv[k] = __ldg(x + min(col, n_cols - 1u));
+    ok[k] = ((uint32_t)k < count);
+  }
 #pragma unroll
   for (int k = 0; k < LEN; k++) {
     if (MODE == ABFT_MODE_CONSTRAINTS) {
@@ -326,23 +339,12 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
       split_value(v[k], w0, w1);
       suspect = or_suspect_bits<MODE>(suspect, w0, w1, c[k]);
     }
-    const uint32_t col = ModeTraits<MODE>::masks_column ? (c[k] & 0x00FFFFFFu) : c[k];
-    // A column no check caught (mode none, or a multi-bit fault the code cannot see) can point outside
-    // vec[]: the reference reads out of bounds there (UB); here, and in the oracle, the column is clamped
-    // to the last entry.
-    ok[k] = ((uint32_t)k < count);
-    xv[k] = __ldg(x + min(col, n_cols - 1u));
   }
-#if ABFT_WALK_UNIFORM
-  // experiment (opt-in): when every row of the warp fills the chunk -- interior rows of a stencil --
-  // the adds need no predicate (the predicated form costs an ISETP and two FSEL per element).  `full` is a
-  // warp-uniform vote taken by the caller; it only picks the code path.
   if (full) {
 #pragma unroll
     for (int k = 0; k < LEN; k++) sum = __dadd_rn(sum, __dmul_rn(v[k], xv[k]));
     return sum;
   }
-#endif
 #pragma unroll
   for (int k = 0; k < LEN; k++) sum = add_if(sum, __dmul_rn(v[k], xv[k]), ok[k]);
   return sum;
@@ -360,85 +362,62 @@ __device__ __forceinline__ bool constraints_fast_ok_row(const uint32_t *cols, ui
   return !__any_sync(0xffffffffu, bad);
 }
 
-// CRC-32C of one 32-bit word appended to a running (raw) state; slicing-by-4 tables
-// tab[s*256 + b] in shared memory.
+// ---- CRC32C row check ---------------------------------------------------------------------------------------------
+// create_matrix (encode.cuh) walks a row with the classic byte tables; the spmv check is organised differently,
+// because 12 byte-table lookups per element, hit by 32 lanes at random, are ~3-way bank conflicted and that alone
+// (41 shared-memory wavefronts per 32 elements) held round 1's kernel at 0.53 of the HBM roofline:
+//  * The raw state after one 32-bit word is F(state ^ word), F = "advance over four zero bytes", a LINEAR map.  Over
+//    one element {w0, w1, col}:  state' = F3(state ^ w0) ^ F2(w1) ^ F(col)  (F2 = F.F, F3 = F.F.F).  Only the first
+//    term is on the row's serial chain: 7 dependent steps per 7-point row instead of 21.
+//  * A linear map of a 32-bit word is the XOR of table entries of its 5-BIT chunks (7 chunks; col has 24 bits: 5).
+//    A 32-entry table laid out one entry per bank is conflict-free whatever the lanes ask for (same entry = same
+//    address = broadcast).  19 conflict-free lookups per element, 21 tables x 128 B = 2.7 KB per CTA.
+__device__ uint32_t g_crc5_tab[kCrcTabWords];  // [(m-1)*7 + j][c], filled by the host at library init
+#ifndef ABFT_CRC_MULHI
+#define ABFT_CRC_MULHI 0
+#endif
+#if ABFT_CRC_MULHI
+__constant__ uint32_t c_crc_mul[8];            // [j] = 2^(34 - 5j): x * it >> 32 == x >> (5j - 2); filled by the host
+#endif
+__device__ uint32_t g_crc_tab[1024];           // slicing-by-4 byte tables (create_matrix), filled by the host at library init
+
+// CRC-32C of one 32-bit word appended to a running (raw) state; slicing-by-4 tables tab[s*256 + b]
 __device__ __forceinline__ uint32_t crc_word(uint32_t crc, uint32_t w, const uint32_t *tab) {
   const uint32_t x = crc ^ w;
   return tab[768 + (x & 0xFF)] ^ tab[512 + ((x >> 8) & 0xFF)] ^ tab[256 + ((x >> 16) & 0xFF)] ^ tab[x >> 24];
 }
 
-__device__ uint32_t g_crc_tab[1024];  // filled by the host at library init
-
-// ---- experiment (opt-in, -DABFT_CRC_CHUNK=5 or 6): bank-conflict-free CRC tables for the spmv check.
-// The byte tables above are hit by 32 lanes at random: ~3.2-way bank conflicts, 41 shared-memory wavefronts per 32
-// elements, and the kernel is bound by exactly that.  The update of the state by one 32-bit word is linear in
-// x = crc ^ word, so x can be cut into chunks of any width B: crc' = xor_j T_j[chunk_j(x)], T_j[c] = F(c << jB) with F =
-// "advance the state over four zero bytes".  With B = 5 (6) the tables have 196 (324) entries in all, small enough to
-// give EVERY LANE ITS OWN COPY IN ITS OWN BANK -- entry e of lane l lives at word e*32 + l -- in 24.5 (40.5) KB of
-// static shared memory: 21 (18) conflict-free lookups per element instead of 12 conflicted ones, 24 (21) wavefronts
-// per 32 elements.  Logic checked on the CPU (tests/test_csr_kernel_logic.py); to be timed in round 2.
-#ifndef ABFT_CRC_CHUNK
-#define ABFT_CRC_CHUNK 0
-#endif
-#if ABFT_CRC_CHUNK
-constexpr int kCrcB = ABFT_CRC_CHUNK;
-constexpr int kCrcChunks = (32 + kCrcB - 1) / kCrcB;
-__host__ __device__ constexpr int crc_chunk_bits(int j) { return (32 - j * kCrcB) < kCrcB ? (32 - j * kCrcB) : kCrcB; }
-__host__ __device__ constexpr int crc_chunk_base(int j) {
-  int b = 0;
-  for (int k = 0; k < j; k++) b += 1 << crc_chunk_bits(k);
-  return b;
-}
-constexpr int kCrcEntries = crc_chunk_base(kCrcChunks);
-constexpr int kCrcSmemWords = kCrcEntries * 32;
-static_assert(kCrcSmemWords * 4 <= 44 * 1024, "chunk tables must fit the static shared-memory budget");
-// T_j[c]: the state four zero bytes after c << jB
-constexpr uint32_t crc_chunk_entry(int j, uint32_t c) {
-  uint32_t x = c << (j * kCrcB);
-  for (int k = 0; k < 4; k++) x = (x >> 8) ^ crc32c_table_entry(x & 0xFFu, 0);
-  return x;
-}
-__device__ uint32_t g_crc_chunk_tab[kCrcEntries];  // filled by the host at library init
-
-// tab = the CTA's table, lane4 = 4 * lane: entry e of this lane is the word at byte offset e*128 + lane4.  Written so
-// that a lookup is shift, and-or (chunk and lane into one offset), load with the table's base as the immediate.
-__device__ __forceinline__ uint32_t crc_word_chunked(uint32_t crc, uint32_t w, const uint32_t *tab, uint32_t lane4) {
-  const uint32_t x = crc ^ w;
+// F^M(x) from the 5-bit chunk tables in shared memory (tab = all 21 tables); NCH chunks of x can be non-zero
+template <int M, int NCH>
+__device__ __forceinline__ uint32_t crc_map(uint32_t x, const uint32_t *tab) {
   uint32_t r = 0;
 #pragma unroll
-  for (int j = 0; j < kCrcChunks; j++) {
-    const int s = j * kCrcB - 7;  // chunk j, times 128, = x shifted by this much and masked
-    const uint32_t shifted = s >= 0 ? (x >> (s >= 0 ? s : 0)) : (x << (s < 0 ? -s : 0));
-    const uint32_t off = (shifted & (((1u << crc_chunk_bits(j)) - 1u) << 7)) | lane4;
-    r ^= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab + crc_chunk_base(j) * 32) + off);
+  for (int j = 0; j < NCH; j++) {
+    // byte offset of entry chunk_j(x) inside its table: the chunk, times 4
+#if ABFT_CRC_MULHI
+    // experiment: the shift as a multiply-high by a power of two the compiler cannot see (IMAD.HI on the FMA pipe, which
+    // this kernel leaves idle, instead of a SHF on the ALU pipe that bounds it)
+    const uint32_t off = (j == 0) ? ((x << 2) & 0x7Cu) : __umulhi(x & (0x1Fu << (5 * j)), c_crc_mul[j]);
+#else
+    const uint32_t off = (j == 0) ? ((x << 2) & 0x7Cu) : ((x >> (5 * j - 2)) & 0x7Cu);
+#endif
+    r ^= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab + ((M - 1) * kCrcChunks + j) * 32) + off);
   }
   return r;
 }
-constexpr int kCrcSpmvWords = kCrcSmemWords;
-#else
-constexpr int kCrcSpmvWords = 1024;
-#endif
 
-// one step of the spmv's row CRC with whichever tables this build uses (`tab`: see the kernel)
-__device__ __forceinline__ uint32_t crc_step(uint32_t crc, uint32_t w, const uint32_t *tab, uint32_t lane4) {
-#if ABFT_CRC_CHUNK
-  return crc_word_chunked(crc, w, tab, lane4);
-#else
-  return crc_word(crc, w, tab);
-#endif
+// the raw state after one more element (col without its top byte)
+__device__ __forceinline__ uint32_t crc_element(uint32_t state, uint32_t w0, uint32_t w1, uint32_t col, const uint32_t *tab) {
+  return crc_map<3, 7>(state ^ w0, tab) ^ crc_map<2, 7>(w1, tab) ^ crc_map<1, 5>(col, tab);
 }
 
-// ---- experiment (opt-in, -DABFT_CRC_WALK=1): an unrolled CRC32C row walk for regular tiles.
-// The shipped CRC path is the generic one-element-at-a-time loop (~110 instructions per element, next to 12 table
-// lookups with ~3-way bank conflicts); this is walk_chunk's shape for the CRC mode: all shared-memory loads, then
-// the serial CRC chain with the gathers in flight beside it, then the products in element order.  For rows of
-// 4..LEN elements (the CRC sits in the top bytes of the first four column words); anything else takes the loop.
-#ifndef ABFT_CRC_WALK
-#define ABFT_CRC_WALK 0
-#endif
+// Unrolled CRC32C row walk for regular tiles, walk_chunk's shape: all shared-memory loads, then per element the
+// gather and the state-independent two thirds of the CRC step, with the serial third (F3) chained through; the
+// products are added in element order.  For rows of 4..LEN elements (the CRC sits in the top bytes of the first
+// four column words); anything else takes the one-by-one loop.
 template <int LEN>
 __device__ __forceinline__ double walk_crc(uint32_t count, const uint32_t *s_cols, const double *s_vals, uint32_t n_cols,
-                                           const double *__restrict__ x, const uint32_t *crc_tab, uint32_t lane4, bool &bad) {
+                                           const double *__restrict__ x, const uint32_t *crc_tab, bool full, bool &bad) {
   uint32_t c[LEN];
   double v[LEN], xv[LEN];
 #pragma unroll
@@ -446,21 +425,25 @@ __device__ __forceinline__ double walk_crc(uint32_t count, const uint32_t *s_col
     c[k] = s_cols[k];
     v[k] = s_vals[k];
   }
-  uint32_t crc = 0xFFFFFFFFu, stored = 0;
+  uint32_t crc = 0xFFFFFFFFu;
 #pragma unroll
   for (int k = 0; k < LEN; k++) {
     const uint32_t col = c[k] & 0x00FFFFFFu;
     xv[k] = __ldg(x + min(col, n_cols - 1u));
-    if (k < 4) stored |= (c[k] >> 24) << (8 * k);  // (count >= 4: these four are the row's own)
     uint32_t w0, w1;
     split_value(v[k], w0, w1);
-    uint32_t next = crc_step(crc, w0, crc_tab, lane4);
-    next = crc_step(next, w1, crc_tab, lane4);
-    next = crc_step(next, col, crc_tab, lane4);
-    crc = ((uint32_t)k < count) ? next : crc;        // slots past the row's end hold the next row's elements
+    const uint32_t next = crc_element(crc, w0, w1, col, crc_tab);
+    crc = (full || (uint32_t)k < count) ? next : crc;        // slots past the row's end hold the next row's elements
   }
+  // (count >= 4: the first four column words are the row's own)
+  const uint32_t stored = __byte_perm(__byte_perm(c[0], c[1], 0x7373), __byte_perm(c[2], c[3], 0x7373), 0x5410);
   bad = (crc ^ 0xFFFFFFFFu) != stored;
   double sum = 0.0;
+  if (full) {
+#pragma unroll
+    for (int k = 0; k < LEN; k++) sum = __dadd_rn(sum, __dmul_rn(v[k], xv[k]));
+    return sum;
+  }
 #pragma unroll
   for (int k = 0; k < LEN; k++) sum = add_if(sum, __dmul_rn(v[k], xv[k]), (uint32_t)k < count);
   return sum;
@@ -471,27 +454,160 @@ struct WaitSpec {
   const CommWindow *me;  // local window
   unsigned int epoch;    // wait until pflag[s] >= epoch ...
   unsigned int mask;     // ... for every rank s in this mask (0: single GPU, no wait)
+  unsigned long long *phase;  // this iteration's row of phase stamps (null: off)
 };
 
-#ifndef ABFT_WALK_UNIFORM
-#define ABFT_WALK_UNIFORM 0
-#endif
-// experiment (opt-in, -DABFT_SPMV_LASTREFILL=1): no CTA barrier per tile in the static kernel.  Every
-// warp counts itself out of a stage when it has finished the tile in it; the warp that is LAST issues the refill of
-// that stage (tile + kStages), so nobody waits for anybody except for data.  Warps may drift up to a tile apart.
-#ifndef ABFT_SPMV_LASTREFILL
-#define ABFT_SPMV_LASTREFILL 0
-#endif
-#if ABFT_SPMV_LASTREFILL && ABFT_ROWS_ECC
-#error "the row-pointer pre-pass needs the per-tile CTA barrier: do not combine ABFT_ROWS_ECC with ABFT_SPMV_LASTREFILL"
-#endif
-#ifndef ABFT_SPMV_MINB
-#define ABFT_SPMV_MINB 4  // resident CTAs per SM the register allocation is tuned for
-#endif
+// Protected row pointers (rowsecc.cuh): check every pair of a staged row-pointer window before anyone looks at it,
+// repair single flips (in the stage and in global memory), strip the check bits; after the next CTA barrier the stage
+// holds plain pointers and the rest of the kernel is unchanged.  The window starts and ends on multiples of four
+// pointers, so pairs are never split; words past rows[n_rows] are zero padding (a valid code word).
+template <int BLOCK>
+__device__ __forceinline__ void rows_prepass(uint32_t *rp, const Tile &t, const MatView &A, const LogRef &L, int tid) {
+  const uint32_t wb = t.row_begin & ~3u;
+  const uint32_t n_words = ((t.row_begin + (t.info & 0xFFFFu) + 1 + 3) & ~3u) - wb;
+  for (uint32_t k = 2 * tid; k + 1 < n_words; k += 2 * BLOCK) {
+    uint32_t w0 = rp[k], w1 = rp[k + 1], bit = 0;
+    const int verdict = rows_check_pair(w0, w1, &bit);
+    const uint32_t pair = (A.row_offset + wb + k) / 2;   // (partitions start on even rows when protected)
+    if (verdict == 1) {
+      log_event(L, ABFT_EV_ROWPTR_CORRECTED, pair, bit);
+      uint32_t *g = const_cast<uint32_t *>(A.rowptr) + wb + k;
+      g[0] = w0;
+      g[1] = w1;
+    } else if (verdict == 2) {
+      log_event(L, ABFT_EV_ROWPTR_DOUBLE, pair, 0);
+    }
+    rp[k] = w0 & kRowsDataMask;
+    rp[k + 1] = w1 & kRowsDataMask;
+  }
+}
+
+// CONSTRAINTS, one row, exactly the reference's checks in the reference's order (CSR/CPUContext.cpp:173-182 row checks,
+// :184-203 element checks); returns the row sum.  s_cols / s_vals: the tile's staged windows (starting at element
+// indices cb / vb); staged_vals_ok = false: the staged values have been overwritten (irregular tiles: by products).
+__device__ __forceinline__ double constraints_careful_row(uint32_t lrow, uint32_t rs, uint32_t re, const Tile &t,
+                                                          const uint32_t *s_cols, const double *s_vals, uint32_t cb,
+                                                          uint32_t vb, bool staged_vals_ok, const MatView &A,
+                                                          const double *__restrict__ x, const LogRef &L) {
+  double sum = 0.0;
+  if (re > A.nnz) log_event(L, ABFT_EV_ROW_SIZE, A.row_offset + lrow, 0);
+  else if (re < rs) log_event(L, ABFT_EV_ROW_ORDER, A.row_offset + lrow, 0);
+  else
+    for (uint32_t i = rs; i < re; i++) {
+      // elements normally sit in the staged window; a corrupted row pointer can send the row
+      // outside it, then go to global memory (i < nnz was checked above)
+      const bool in = (i >= t.nnz_begin) && (i < t.nnz_end);
+      const uint32_t col = in ? s_cols[i - cb] : A.cols[i];
+      if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + lrow); break; }
+      if (i < re - 1) {
+        const bool in2 = (i + 1 >= t.nnz_begin) && (i + 1 < t.nnz_end);
+        const uint32_t nxt = in2 ? s_cols[i + 1 - cb] : A.cols[i + 1];
+        if (nxt <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + lrow); break; }
+      }
+      const double val = (in && staged_vals_ok) ? s_vals[i - vb] : A.values[i];
+      sum = __dadd_rn(sum, __dmul_rn(val, __ldg(x + col)));
+    }
+  return sum;
+}
+
+// One row of a regular tile per lane, straight from the staged stream (WARP-COLLECTIVE: every lane of the warp calls it,
+// lanes without a row with has_row = false).  `k` = the lane's row number inside the tile.  Writes y[row] and adds the
+// row's share of dot(vec, result) to dot_part.
+template <int MODE>
+__device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_row, const uint32_t *s_rptr,
+                                            const uint32_t *s_cols, const double *s_vals, const MatView &A,
+                                            const double *__restrict__ x, double *__restrict__ y, const LogRef &L,
+                                            const uint32_t *s_crc, double &dot_part) {
+  const uint32_t rb = t.row_begin & ~3u, cb = t.nnz_begin & ~3u, vb = t.nnz_begin & ~1u;
+  const uint32_t row = t.row_begin + k;
+  const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the tile
+  const uint32_t need = max_len <= 4 ? 4u : max_len;               // the unrolled walk's length
+  uint32_t rs = 0, re = 0;
+  double xrow = 0.0;
+  if (has_row) {
+    rs = s_rptr[row - rb];
+    re = s_rptr[row + 1 - rb];
+    xrow = __ldg(x + A.row_offset + row);   // dot()'s operand: in flight behind the walk, not after it
+    if (MODE != ABFT_MODE_CONSTRAINTS) {
+      // these modes trust rows[] like the reference; clamp so a bad pointer cannot fault
+      rs = min(max(rs, t.nnz_begin), t.nnz_end);
+      re = min(max(re, rs), t.nnz_end);
+    }
+  }
+  const uint32_t len = re - rs;
+  // (CONSTRAINTS: only if its row pointers keep the row inside the staged window; anything else,
+  // i.e. a corrupted rows[], takes the careful path that mirrors the reference's checks one by one)
+  const bool in_window = MODE != ABFT_MODE_CONSTRAINTS || (rs >= t.nnz_begin && re <= t.nnz_end && rs <= re);
+  // does every row of this warp fill the unrolled walk?  Lanes without a row do not veto.
+  const bool full_rows = max_len <= 7 && __all_sync(0xffffffffu, !has_row || (in_window && len == need));
+  if (!has_row) return;
+  double sum = 0.0;
+  bool careful = true;
+  const uint32_t *sc = s_cols + (rs - cb);
+  const double *sv = s_vals + (rs - vb);
+  if (MODE != ABFT_MODE_CRC32C && in_window) {
+    uint32_t suspect = 0;
+    // max_len is what create_matrix saw.  A corrupted rows[] can make this row longer while keeping it inside
+    // the window; the reference walks the whole [start, end) range (CSR/CPUContext.cpp:125,184), so such a
+    // row goes down the one-by-one path instead of an unrolled walk that would stop after max_len elements.
+    if (max_len <= 7 && len > need) suspect = 1u;
+    else if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
+    else if (max_len == 5) sum = walk_chunk<MODE, 5>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
+    else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
+    else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
+    else
+      // longer rows: chunks of 4 up to this row's own length (never more than 3 slots past its end,
+      // which the over-staged window covers; the trip count may differ between lanes)
+      for (uint32_t base = 0; base < len; base += 4)
+        sum = walk_chunk<MODE, 4>(sum, base, len - base, sc, sv, A.n_cols, x, suspect);
+    careful = (suspect & 1u) != 0;  // a check tripped somewhere in this row: walk it again, carefully
+  }
+  if (MODE == ABFT_MODE_CRC32C && max_len <= 7 && len >= 4 && len <= need) {
+    bool bad = false;
+    if (max_len <= 4) sum = walk_crc<4>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
+    else if (max_len == 5) sum = walk_crc<5>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
+    else if (max_len == 6) sum = walk_crc<6>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
+    else sum = walk_crc<7>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
+    if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
+    careful = false;
+  }
+  if (careful) {
+    sum = 0.0;
+    if (MODE == ABFT_MODE_CONSTRAINTS) {
+      sum = constraints_careful_row(row, rs, re, t, s_cols, s_vals, cb, vb, true, A, x, L);
+    } else if (MODE == ABFT_MODE_CRC32C) {
+      uint32_t crc = 0xFFFFFFFFu, stored = 0;
+      bool bad = false;
+      for (uint32_t i = rs; i < re; i++) {
+        const uint32_t cw = s_cols[i - cb];
+        const double val = s_vals[i - vb];
+        uint32_t w0, w1;
+        split_value(val, w0, w1);
+        if (len >= 4) {
+          if (i - rs < 4) stored |= (cw >> 24) << (8 * (i - rs));
+          crc = crc_element(crc, w0, w1, cw & 0x00FFFFFFu, s_crc);
+        } else {
+          // too short to hold 32 CRC bits: SECDED check byte per element, detect-only
+          if ((overall_parity(w0, w1, cw) | syndrome7_any(w0, w1, cw)) & 1u) bad = true;
+        }
+        sum = __dadd_rn(sum, element_product<MODE>(cw, val, i, A, x, L));
+      }
+      if (len >= 4 && (crc ^ 0xFFFFFFFFu) != stored) bad = true;
+      if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
+    } else {
+      // element by element, repairing / reporting as the mode demands (the owning thread
+      // writes a corrected element back)
+      for (uint32_t i = rs; i < re; i++)
+        sum = __dadd_rn(sum, element_product<MODE>(s_cols[i - cb], s_vals[i - vb], i, A, x, L));
+    }
+  }
+  y[row] = sum;
+  dot_part = __dadd_rn(dot_part, __dmul_rn(sum, xrow));
+}
 
 // DYN: the dynamic tile schedule (A.tile_counter), compiled as its own kernel so that the static one carries none of it
 template <int MODE, bool DYN>
-__global__ void __launch_bounds__(kBlock, (MODE == ABFT_MODE_CRC32C) ? 3 : ABFT_SPMV_MINB)
+__global__ void __launch_bounds__(SpmvCfg<DYN>::block, (MODE == ABFT_MODE_CRC32C ? 3 : 4) * (kBlock / SpmvCfg<DYN>::block))
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
             const int *__restrict__ active, WaitSpec wait) {
 #ifndef ABFT_HOST_EMU
@@ -499,17 +615,17 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
 #else
   unsigned char *const dyn_smem = emu::g_dyn_smem;
 #endif
+  constexpr int BLOCK = SpmvCfg<DYN>::block;
+  constexpr int kWarps = BLOCK / 32;
   using StageBuf = typename SpmvCfg<DYN>::Stage;
   constexpr size_t kSpmvDynSmem = SpmvCfg<DYN>::dyn_smem;
   StageBuf *stage = reinterpret_cast<StageBuf *>(dyn_smem);
   __shared__ __align__(8) uint64_t s_full[kStages];
   __shared__ Tile s_tile[kStages];
   __shared__ uint32_t s_tidx[kStages];              // index of the staged tile (dynamic schedule: its partial's slot)
-  __shared__ unsigned int s_done[kStages];          // ABFT_SPMV_LASTREFILL: warps that have finished the tile in a stage
-  constexpr bool last_refill = ABFT_SPMV_LASTREFILL && !DYN;
-  __shared__ double s_wdot[2][kBlock / 32];         // dynamic schedule: the warps' dot() partials of a tile
-  __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? kCrcSpmvWords : 1];
-  __shared__ double s_warp[kBlock / 32];
+  __shared__ double s_wdot[2][kWarps];              // dynamic schedule: the warps' dot() partials of a tile
+  __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? kCrcTabWords : 1];
+  __shared__ double s_warp[kWarps];
 
   if (active && *active == 0) return;  // device-resident loop already converged
 
@@ -535,7 +651,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     // the row walk may look a few slots past the data TMA delivers: start from all-zero buffers
     // (a zero element is a valid code word in every mode)
     uint4 *z = reinterpret_cast<uint4 *>(dyn_smem);
-    for (uint32_t i = tid; i < kSpmvDynSmem / 16; i += kBlock) z[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < kSpmvDynSmem / 16; i += BLOCK) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) mbar_init(&s_full[s], 1);
@@ -544,12 +660,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   __syncthreads();
   if (tid == 0) fence_proxy_async();
   if (MODE == ABFT_MODE_CRC32C)
-#if ABFT_CRC_CHUNK
-    for (int i = tid; i < kCrcSmemWords; i += kBlock) s_crc[i] = g_crc_chunk_tab[i >> 5];  // one copy per lane / bank
-#else
-    for (int i = tid; i < 1024; i += kBlock) s_crc[i] = g_crc_tab[i];
-#endif
-  const uint32_t crc_lane4 = (threadIdx.x & 31u) * 4u;  // (chunked tables: this lane's copy)
+    for (int i = tid; i < kCrcTabWords; i += BLOCK) s_crc[i] = g_crc5_tab[i];
   __syncthreads();
 
   const uint64_t stream_policy = l2_evict_first_policy();
@@ -576,18 +687,20 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     }
   };
 
+  // (Tried in round 2 and removed: splitting the refill over the eight warps -- every warp's lane 0 streaming one part
+  // of the tile and arriving on the stage's mbarrier -- so that no single warp reaches the per-tile CTA barrier ~90
+  // instructions late.  It did what it was meant to, ncu: barrier stall 1.84 -> 0.69 warps per issue cycle, but the
+  // part bookkeeping cost every warp ~75 instructions per tile: 219 M -> 259 M warp instructions and 0.33 -> 0.37 ms.
+  // This kernel's time follows its instruction count, profiles/r2_ab_session4_split_refill.jsonl.)
   if (tid == 0) {
-    // (last_refill: every stage is filled up front; afterwards a stage is refilled by the warp that leaves it last)
-    for (int j = 0; j + (last_refill ? 0 : 1) < kStages; j++) {
-      fetch_ahead();
-      s_tile[j] = ahead;
-      s_tidx[j] = ahead_idx;
-      s_done[j] = 0u;
-      if (ahead.info != kTileNone) issue(j, ahead);
-      else mbar_arrive(&s_full[j]);  // nothing to stream: complete the phase so the waiters get to see the marker
-    }
-    if (!last_refill) fetch_ahead();
+    fetch_ahead();
+    s_tile[0] = ahead;
+    s_tidx[0] = ahead_idx;
+    if (ahead.info != kTileNone) issue(0, ahead);
+    else mbar_arrive(&s_full[0]);  // nothing to stream: complete the phase so the waiters get to see the marker
+    fetch_ahead();
   }
+  if (tid == 0 && blockIdx.x == 0) phase_stamp(wait.phase, PH_SPMV_BEGIN);
   if (wait.mask) {
     // the matrix stream of the first tile is already in flight; vec[] is only touched after this
     if (tid == 0) {
@@ -598,7 +711,15 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
       __threadfence_system();
     }
   }
+  if (tid == 0 && blockIdx.x == 0) phase_stamp(wait.phase, PH_SPMV_WAIT_END);
   __syncthreads();
+  if (A.rows_ecc) {
+    // the first tile's row pointers; those of tile it + 1 are checked at the end of iteration it, behind the walk
+    mbar_wait(&s_full[0], 0u);
+    const Tile t0 = s_tile[0];
+    if (t0.info != kTileNone) rows_prepass<BLOCK>(stage[0].rptr, t0, A, L, tid);
+    __syncthreads();
+  }
 
   double dot_part = 0.0;
 
@@ -606,13 +727,13 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   for (; DYN || it < n_my; it++) {
     const int st = (int)(it % kStages);
     // thread 0: bank the previous tile's dot() partial (dynamic schedule), refill the stage that tile released
-    if (tid == 0 && !last_refill) {
+    if (tid == 0) {
       if (dynamic && it > 0) {
         // the warps' sums, added in warp order
         const double *wd = s_wdot[(it - 1) & 1u];
         double tp = wd[0];
 #pragma unroll
-        for (int k = 1; k < kBlock / 32; k++) tp = __dadd_rn(tp, wd[k]);
+        for (int k = 1; k < kWarps; k++) tp = __dadd_rn(tp, wd[k]);
         red.partials[s_tidx[(it - 1) % kStages]] = tp;
       }
       const int js = (int)((it + kStages - 1) % kStages);
@@ -630,39 +751,11 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     if (DYN && t.info == kTileNone) break;
     const bool irregular_tile = !(t.info & (kTileLongRow | kTileRegular)) && MODE != ABFT_MODE_CRC32C;
     const StageBuf &B = stage[st];
-#if ABFT_ROWS_ECC
-    if (A.rows_ecc) {
-      // Protected row pointers (rowsecc.cuh): check every pair of the staged window before anyone looks at it, repair
-      // single flips (in the stage and in global memory), strip the check bits.  After the barrier the stage holds
-      // plain pointers and the rest of the kernel is unchanged.  The window starts and ends on multiples of four
-      // pointers, so pairs are never split; words past rows[n_rows] are zero padding (a valid code word).
-      uint32_t *rp = const_cast<uint32_t *>(B.rptr);
-      const uint32_t wb = t.row_begin & ~3u;
-      const uint32_t n_words = ((t.row_begin + (t.info & 0xFFFFu) + 1 + 3) & ~3u) - wb;
-      for (uint32_t k = 2 * tid; k + 1 < n_words; k += 2 * kBlock) {
-        uint32_t w0 = rp[k], w1 = rp[k + 1], bit = 0;
-        const int verdict = rows_check_pair(w0, w1, &bit);
-        const uint32_t pair = (A.row_offset + wb + k) / 2;   // (partitions start on even rows when protected)
-        if (verdict == 1) {
-          log_event(L, ABFT_EV_ROWPTR_CORRECTED, pair, bit);
-          uint32_t *g = const_cast<uint32_t *>(A.rowptr) + wb + k;
-          g[0] = w0;
-          g[1] = w1;
-        } else if (verdict == 2) {
-          log_event(L, ABFT_EV_ROWPTR_DOUBLE, pair, 0);
-        }
-        rp[k] = w0 & kRowsDataMask;
-        rp[k + 1] = w1 & kRowsDataMask;
-      }
-      __syncthreads();
-    }
-#endif
     if (dynamic) dot_part = 0.0;  // reduced per tile below
     const uint32_t nrows = t.info & 0xFFFFu;
     const uint32_t n = t.nnz_end - t.nnz_begin;
     const uint32_t rb = t.row_begin & ~3u, cb = t.nnz_begin & ~3u, vb = t.nnz_begin & ~1u;
     const bool has_row = (uint32_t)tid < nrows;
-    const uint32_t row = t.row_begin + tid;
 
     if (t.info & kTileLongRow) {
       // ---------------- one long row: stream it from global memory in chunks ----------------
@@ -689,14 +782,14 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
             }
         }
       }
-      for (uint32_t base = tid; !moved && base < n; base += kLongBatch * kBlock) {
+      for (uint32_t base = tid; !moved && base < n; base += kLongBatch * BLOCK) {
         uint32_t li[kLongBatch], cw[kLongBatch];
         double val[kLongBatch], pr[kLongBatch];
         bool ok[kLongBatch];
 #pragma unroll
         for (int k = 0; k < kLongBatch; k++) {
-          ok[k] = (k == 0) || (base + k * kBlock < n);
-          li[k] = t.nnz_begin + (ok[k] ? base + k * kBlock : base);
+          ok[k] = (k == 0) || (base + k * BLOCK < n);
+          li[k] = t.nnz_begin + (ok[k] ? base + k * BLOCK : base);
           cw[k] = ld_stream(A.cols + li[k]);
           val[k] = ld_stream(A.values + li[k]);
         }
@@ -722,69 +815,28 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           uint32_t w0, w1;
           split_value(A.values[i], w0, w1);
           if (e < 4) stored |= (cw >> 24) << (8 * e);
-          crc = crc_step(crc, w0, s_crc, crc_lane4);
-          crc = crc_step(crc, w1, s_crc, crc_lane4);
-          crc = crc_step(crc, cw & 0x00FFFFFFu, s_crc, crc_lane4);
+          crc = crc_element(crc, w0, w1, cw & 0x00FFFFFFu, s_crc);
         }
         if ((crc ^ 0xFFFFFFFFu) != stored) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + t.row_begin, 0);
       }
-      const double total = block_sum(acc, s_warp);
+      const double total = block_sum<BLOCK>(acc, s_warp);
       if (tid == 0) {
         y[t.row_begin] = total;
         dot_part = __dadd_rn(dot_part, __dmul_rn(total, x[A.row_offset + t.row_begin]));
       }
     } else {
       const bool irregular = irregular_tile;
-      // CONSTRAINTS, one row, exactly the reference's checks in the reference's order
-      // (CSR/CPUContext.cpp:173-182 row checks, :184-203 element checks); returns the row sum
       auto constraints_careful = [&](uint32_t grow, uint32_t rs, uint32_t re) -> double {
-        double sum = 0.0;
-        if (re > A.nnz) log_event(L, ABFT_EV_ROW_SIZE, A.row_offset + grow, 0);
-        else if (re < rs) log_event(L, ABFT_EV_ROW_ORDER, A.row_offset + grow, 0);
-        else
-          for (uint32_t i = rs; i < re; i++) {
-            // elements normally sit in the staged window; a corrupted row pointer can send the row
-            // outside it, then go to global memory (i < nnz was checked above)
-            const bool in = (i >= t.nnz_begin) && (i < t.nnz_end);
-            const uint32_t col = in ? B.cols[i - cb] : A.cols[i];
-            if (col >= A.n_cols) { log_event(L, ABFT_EV_COL_SIZE, A.nnz_offset + i, A.row_offset + grow); break; }
-            if (i < re - 1) {
-              const bool in2 = (i + 1 >= t.nnz_begin) && (i + 1 < t.nnz_end);
-              const uint32_t nxt = in2 ? B.cols[i + 1 - cb] : A.cols[i + 1];
-              if (nxt <= col) { log_event(L, ABFT_EV_COL_ORDER, A.nnz_offset + i, A.row_offset + grow); break; }
-            }
-            // (the staged values of an irregular tile have been overwritten by products)
-            const double val = (in && !irregular) ? B.vals[i - vb] : A.values[i];
-            sum = __dadd_rn(sum, __dmul_rn(val, __ldg(x + col)));
-          }
-        return sum;
+        return constraints_careful_row(grow, rs, re, t, B.cols, B.vals, cb, vb, !irregular, A, x, L);
       };
-      bool full_rows = false;
-#if ABFT_WALK_UNIFORM
-      if (!irregular && MODE != ABFT_MODE_CRC32C) {  // (uniform over the CTA)
-        // does every row of this warp fill the unrolled walk?  Lanes without a row do not veto.
-        const uint32_t ml = (t.info >> kTileMaxLenShift) & 0xFFFu;
-        const uint32_t need = ml <= 4 ? 4u : ml;
-        bool mine = true;
-        if (has_row) {
-          uint32_t a = B.rptr[row - rb], b = B.rptr[row + 1 - rb];
-          if (MODE != ABFT_MODE_CONSTRAINTS) {  // the same clamp as the walk below
-            a = min(max(a, t.nnz_begin), t.nnz_end);
-            b = min(max(b, a), t.nnz_end);
-          }
-          mine = b >= a && b - a >= need;
-        }
-        full_rows = __all_sync(0xffffffffu, mine) && ml <= 7;
-      }
-#endif
       if (irregular) {
         // ---------------- irregular tile ----------------
         // The tile's rows are dealt to the warps in equal runs of consecutive rows (warp w owns rows
-        // [w*c, (w+1)*c), c = ceil(nrows / 8) <= 32, one per lane), so every warp has its share whatever the tile's
+        // [w*c, (w+1)*c), c = ceil(nrows / warps) <= 32, one per lane), so every warp has its share whatever the tile's
         // row count, and a warp finishes its own rows -- short and long -- without a CTA-wide barrier.  The dot()
         // operand is fetched now, ahead of the element phase.
         const int lane = tid & 31, warp = tid >> 5;
-        const uint32_t per_warp = (nrows + kBlock / 32 - 1) / (kBlock / 32);
+        const uint32_t per_warp = (nrows + kWarps - 1) / kWarps;
         const uint32_t q = (uint32_t)warp * per_warp + lane;
         const bool has_q = (uint32_t)lane < per_warp && q < nrows;
         const uint32_t qrow = t.row_begin + q;
@@ -794,15 +846,15 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         // shared-memory loads, then all checks and gathers, then the stores.  The checks only OR their verdict
         // into `suspect`; a batch that trips goes through element_product one element at a time (rare).
         double *prod = const_cast<double *>(B.vals);
-        for (uint32_t e0 = tid; e0 < n; e0 += kElemBatch * kBlock) {
+        for (uint32_t e0 = tid; e0 < n; e0 += kElemBatch * BLOCK) {
           uint32_t li[kElemBatch], cw[kElemBatch];
           double v[kElemBatch], pr[kElemBatch];
           bool ok[kElemBatch];
 #pragma unroll
           for (int k = 0; k < kElemBatch; k++) {
             // slots past the tile's end repeat this thread's first element (loaded, checked, never stored)
-            ok[k] = (k == 0) || (e0 + k * kBlock < n);
-            li[k] = t.nnz_begin + (ok[k] ? e0 + k * kBlock : e0);
+            ok[k] = (k == 0) || (e0 + k * BLOCK < n);
+            li[k] = t.nnz_begin + (ok[k] ? e0 + k * BLOCK : e0);
             cw[k] = B.cols[li[k] - cb];
             v[k] = B.vals[li[k] - vb];
           }
@@ -873,129 +925,31 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           y[qrow] = sum;
           dot_part = __dadd_rn(dot_part, __dmul_rn(sum, xq));
         }
-      } else if (has_row) {
-        uint32_t rs = B.rptr[row - rb], re = B.rptr[row + 1 - rb];
-        double sum = 0.0;
-        bool careful = true;
-        if (MODE != ABFT_MODE_CONSTRAINTS) {
-          // these modes trust rows[] like the reference; clamp so a bad pointer cannot fault
-          rs = min(max(rs, t.nnz_begin), t.nnz_end);
-          re = min(max(re, rs), t.nnz_end);
-        }
+      } else {
         // ---------------- regular tile: thread-per-row straight from the staged stream ----------------
-        // (CONSTRAINTS only if its row pointers keep the row inside the staged window; anything else,
-        // i.e. a corrupted rows[], takes the careful path that mirrors the reference's checks one by one)
-        if (MODE != ABFT_MODE_CRC32C &&
-            (MODE != ABFT_MODE_CONSTRAINTS || (rs >= t.nnz_begin && re <= t.nnz_end && rs <= re))) {
-          const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the CTA
-          const uint32_t len = re - rs;
-          const uint32_t *sc = B.cols + (rs - cb);
-          const double *sv = B.vals + (rs - vb);
-          uint32_t suspect = 0;
-          // max_len is what create_matrix saw.  A corrupted rows[] can make this row longer while keeping it inside
-          // the window; the reference walks the whole [start, end) range (CSR/CPUContext.cpp:125,184), so such a
-          // row goes down the one-by-one path instead of an unrolled walk that would stop after max_len elements.
-          if (max_len <= 7 && len > (max_len <= 4 ? 4u : max_len)) suspect = 1u;
-          else if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
-          else if (max_len == 5) sum = walk_chunk<MODE, 5>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
-          else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
-          else if (max_len == 7) sum = walk_chunk<MODE, 7>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
-          else
-            // longer rows: chunks of 4 up to this row's own length (never more than 3 slots past its end,
-            // which the over-staged window covers; the trip count may differ between lanes)
-            for (uint32_t base = 0; base < len; base += 4)
-              sum = walk_chunk<MODE, 4>(sum, base, len - base, sc, sv, A.n_cols, x, suspect);
-          careful = (suspect & 1u) != 0;  // a check tripped somewhere in this row: walk it again, carefully
-        }
-#if ABFT_CRC_WALK
-        if (MODE == ABFT_MODE_CRC32C) {
-          const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the CTA
-          const uint32_t len = re - rs;
-          if (max_len <= 7 && len >= 4 && len <= (max_len <= 4 ? 4u : max_len)) {
-            const uint32_t *sc = B.cols + (rs - cb);
-            const double *sv = B.vals + (rs - vb);
-            bool bad = false;
-            if (max_len <= 4) sum = walk_crc<4>(len, sc, sv, A.n_cols, x, s_crc, crc_lane4, bad);
-            else if (max_len == 5) sum = walk_crc<5>(len, sc, sv, A.n_cols, x, s_crc, crc_lane4, bad);
-            else if (max_len == 6) sum = walk_crc<6>(len, sc, sv, A.n_cols, x, s_crc, crc_lane4, bad);
-            else sum = walk_crc<7>(len, sc, sv, A.n_cols, x, s_crc, crc_lane4, bad);
-            if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
-            careful = false;
-          }
-        }
-#endif
-        if (careful) {
-          sum = 0.0;
-          if (MODE == ABFT_MODE_CONSTRAINTS) {
-            sum = constraints_careful(row, rs, re);
-          } else if (MODE == ABFT_MODE_CRC32C) {
-            const uint32_t len = re - rs;
-            uint32_t crc = 0xFFFFFFFFu, stored = 0;
-            bool bad = false;
-            for (uint32_t i = rs; i < re; i++) {
-              const uint32_t cw = B.cols[i - cb];
-              const double val = B.vals[i - vb];
-              uint32_t w0, w1;
-              split_value(val, w0, w1);
-              if (len >= 4) {
-                if (i - rs < 4) stored |= (cw >> 24) << (8 * (i - rs));
-                crc = crc_step(crc, w0, s_crc, crc_lane4);
-                crc = crc_step(crc, w1, s_crc, crc_lane4);
-                crc = crc_step(crc, cw & 0x00FFFFFFu, s_crc, crc_lane4);
-              } else {
-                // too short to hold 32 CRC bits: SECDED check byte per element, detect-only
-                if ((overall_parity(w0, w1, cw) | syndrome7_any(w0, w1, cw)) & 1u) bad = true;
-              }
-              sum = __dadd_rn(sum, element_product<MODE>(cw, val, i, A, x, L));
-            }
-            if (len >= 4 && (crc ^ 0xFFFFFFFFu) != stored) bad = true;
-            if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
-          } else {
-            // element by element, repairing / reporting as the mode demands (the owning thread
-            // writes a corrected element back)
-            for (uint32_t i = rs; i < re; i++)
-              sum = __dadd_rn(sum, element_product<MODE>(B.cols[i - cb], B.vals[i - vb], i, A, x, L));
-          }
-        }
-        y[row] = sum;
-        dot_part = __dadd_rn(dot_part, __dmul_rn(sum, x[A.row_offset + row]));
+        regular_row<MODE>(t, (uint32_t)tid, has_row, B.rptr, B.cols, B.vals, A, x, y, L, s_crc, dot_part);
       }
     }
     if (dynamic) {
       const double wp = warp_sum(dot_part);
       if ((tid & 31) == 0) s_wdot[it & 1u][tid >> 5] = wp;
     }
-#if ABFT_SPMV_LASTREFILL
-    if (last_refill) {
-      // this warp is done with stage `st`; the warp that is last to say so refills it with tile it + kStages
-      __syncwarp();
-      if ((tid & 31) == 0) {
-        __threadfence_block();  // (release: this warp's reads of the stage are behind it)
-        const unsigned int before = atomicAdd(&s_done[st], 1u);
-        if (before == kBlock / 32 - 1) {
-          __threadfence_block();  // (acquire: so are everybody else's)
-          s_done[st] = 0u;
-          const uint32_t nxt = it + kStages;
-          if (nxt < n_my) {
-            const uint32_t idx = blockIdx.x + nxt * G;
-            const Tile tn = A.tiles[idx];
-            s_tile[st] = tn;
-            s_tidx[st] = idx;
-            issue(st, tn);
-          }
-        }
-      }
-    } else
-#endif
-    {
-      __syncthreads();  // everyone is done with stage `st`: it may be refilled
+    if (A.rows_ecc) {
+      // the NEXT tile's row pointers (its stream was issued at the top of this iteration and has normally landed
+      // behind the walk): checked here so that the barrier below also publishes the repaired, stripped pointers
+      const int sn = (int)((it + 1) % kStages);
+      mbar_wait(&s_full[sn], ((it + 1) / kStages) & 1u);
+      const Tile tn = s_tile[sn];
+      if (tn.info != kTileNone && (DYN || it + 1 < n_my)) rows_prepass<BLOCK>(stage[sn].rptr, tn, A, L, tid);
     }
+    __syncthreads();  // everyone is done with stage `st`: it may be refilled
   }
   // (dynamic schedule: the loop only ends at the marker, whose iteration has already banked the last tile's partial)
   // fused dot(vec, result): CTA partials (static) or the per-tile partials (dynamic), then the grid-wide deterministic sum
-  const double mine = dynamic ? 0.0 : block_sum(dot_part, s_warp);
-  const bool last = grid_sum_finalize(mine, red, s_warp, dynamic ? A.n_tiles : 0u);
+  const double mine = dynamic ? 0.0 : block_sum<BLOCK>(dot_part, s_warp);
+  const bool last = grid_sum_finalize<BLOCK>(mine, red, s_warp, dynamic ? A.n_tiles : 0u);
   if (dynamic && last && tid == 0) *A.tile_counter = 0u;  // every CTA has drawn its last tile: ready for the next launch
 }
+
 
 }  // namespace abft

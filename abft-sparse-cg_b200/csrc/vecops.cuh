@@ -59,6 +59,7 @@ calc_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__r
     if (red.active && blockIdx.x == 0 && threadIdx.x == 0) *red.active = 0;
     return;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) phase_stamp(red.phase, PH_XR_BEGIN);
   const double alpha = scalar_of<DEV>(alpha_arg);
   const int n2 = vec_ok ? (N >> 1) : 0;
   double2 *x2 = reinterpret_cast<double2 *>(x);
@@ -129,6 +130,7 @@ struct PushPlan {
   int world, rank;
   int row0;            // global row of local element 0
   unsigned int epoch;  // published in the peers' pflag[rank] once every store has landed
+  unsigned long long *phase;  // this iteration's row of phase stamps (null: off)
 };
 
 template <bool DEV, bool COMPUTE>
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(kBlock)
 calc_p_push_kernel(double *__restrict__ p, const double *__restrict__ r, ScalarArg beta_arg, int N, PushPlan plan,
                    const int *__restrict__ active) {
   if (active && *active == 0) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) phase_stamp(plan.phase, PH_P_BEGIN);
   const double beta = COMPUTE ? scalar_of<DEV>(beta_arg) : 0.0;
   constexpr int kPer = 8;
   constexpr int kChunk = kBlock * kPer;
@@ -179,6 +182,7 @@ calc_p_push_kernel(double *__restrict__ p, const double *__restrict__ r, ScalarA
       for (int s = 0; s < plan.world; s++)
         if (s != plan.rank && plan.hi[s] > plan.lo[s])
           *reinterpret_cast<volatile unsigned int *>(&plan.win[s]->pflag[plan.rank]) = plan.epoch;
+      phase_stamp(plan.phase, PH_P_END);
     }
   }
 }

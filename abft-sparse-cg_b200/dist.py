@@ -155,6 +155,18 @@ class DistCG:
         self.rr = rr
         return done
 
+    def host_loop(self, k: int, conv: float = 0.0) -> int:
+        """iterate(), compiled (abft_cuda_dist_cg_host_loop: the same four dist_* calls per iteration)."""
+        rr = C.c_double(self.rr)
+        n = self.L.abft_cuda_dist_cg_host_loop(self.ctx.ctx, self.comm, self.A.handle, self.x.handle, self.r.handle,
+                                               self.p.handle, self.p_full.handle, self.w.handle, int(k), float(conv),
+                                               C.byref(rr), None)
+        if n < 0:
+            from . import capi
+            raise RuntimeError("cuda target: dist_cg_host_loop failed: " + capi.last_error())
+        self.rr = rr.value
+        return n
+
     def solve_device(self, max_itrs: int, conv: float, check_every: int = 32):
         """Device-resident loop (abft_cuda_dist_cg_solve): r = b, p = r, then iterate; -> (iterations, rr)."""
         rr = C.c_double(0.0)

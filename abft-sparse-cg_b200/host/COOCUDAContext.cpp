@@ -133,18 +133,19 @@ class COOCUDAContext : public CGContext {
   void report_faults() {
     if (!abft_cuda_events_pending(ctx)) return;
     abft_event ev[256];
-    int fatal = 0;
-    const int n = abft_cuda_poll_events(ctx, ev, 256, &fatal);
+    int fatal = 0, n;
+    while ((n = abft_cuda_poll_events(ctx, ev, 256, &fatal)) > 0) {  // (handed out 256 at a time until drained)
+      char line[160];
+      for (int i = 0; i < n; i++) {
+        abft_cuda_coo_format_event(&ev[i], line, sizeof line);
+        printf("%s\n", line);
+      }
+      if (fatal) {
+        fflush(stdout);
+        exit(1);
+      }
+    }
     if (n < 0) die("poll_events");
-    char line[160];
-    for (int i = 0; i < n; i++) {
-      abft_cuda_coo_format_event(&ev[i], line, sizeof line);
-      printf("%s\n", line);
-    }
-    if (fatal) {
-      fflush(stdout);
-      exit(1);
-    }
   }
 };
 

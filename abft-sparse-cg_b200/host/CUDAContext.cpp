@@ -335,18 +335,19 @@ class CUDAContext : public CGContext {
     if (!events_pending()) return;
     for (int d = 0; d < G; d++) {
       abft_event ev[256];
-      int fatal = 0;
-      int n = abft_cuda_poll_events(ctx[d], ev, 256, &fatal);
+      int fatal = 0, n;
+      while ((n = abft_cuda_poll_events(ctx[d], ev, 256, &fatal)) > 0) {  // (handed out 256 at a time until drained)
+        char line[128];
+        for (int i = 0; i < n; i++) {
+          abft_cuda_format_event(&ev[i], line, sizeof line);
+          printf("%s\n", line);
+        }
+        if (fatal) {
+          fflush(stdout);
+          exit(1);
+        }
+      }
       if (n < 0) die("poll_events");
-      char line[128];
-      for (int i = 0; i < n; i++) {
-        abft_cuda_format_event(&ev[i], line, sizeof line);
-        printf("%s\n", line);
-      }
-      if (fatal) {
-        fflush(stdout);
-        exit(1);
-      }
     }
   }
 

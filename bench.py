@@ -4,20 +4,34 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--mode secded] [--grid 256] [--impl ours|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one CG iteration (cg.cpp:94-118): spmv (+ fused dot), calc_xr, calc_p, driven through the
-C ABI exactly as the CGContext plugin drives it (two host-visible scalars per iteration).
+A "step" is one CG iteration (cg.cpp:94-118): spmv (+ fused dot), calc_xr, calc_p, driven through the C ABI
+exactly as the CGContext plugin drives it -- four calls, two host-visible scalars per iteration.
 
 Workload (config.workload): 3D 7-point Poisson on a grid^3 mesh (default 256^3: N = 2^24, nnz = 117 047 296,
-BASELINE.json configs[2] / the north_star's ">= 100M non-zeros" roofline case), ABFT mode `secded` unless
---mode says otherwise, right-hand side uniform in [0,1) like cg.cpp:70.  Synthetic, generated in memory in the
-triplet order cg.cpp hands to create_matrix.  At N > 1 the rows are partitioned across ranks (strong scaling:
-the matrix is fixed), the search direction p is all-gathered over NCCL and the two scalars are all-reduced.
+BASELINE.json configs[2] / the north_star's ">= 100M non-zeros" roofline case), ABFT mode `secded` unless --mode
+says otherwise, right-hand side uniform in [0,1) like cg.cpp:70.  Synthetic, generated in memory in the triplet
+order cg.cpp hands to create_matrix.  At N > 1 the rows are partitioned across ranks (strong scaling: the matrix is
+fixed); the halo of the search direction p is stored into the peers' copies over NVLink by calc_p itself and the
+two scalars are all-reduced through peer memory inside the reductions (CUDA IPC; torch.distributed / NCCL carries
+only the setup and the timing barrier, nothing on the data path).
 
-Printed JSON keys follow the driver's contract; see DESIGN.md "Measurement" for the definitions of
-value / e2e / roofline / cpu_baseline used here.
+What the JSON line holds:
+  value                  K / median over --blocks timed blocks of K iterations each, every block bracketed by
+                         barrier + synchronize, CUDA events on the context's stream, max over ranks; the PLUGIN path
+                         (host-driven four-call loop), operands resident in HBM.  `blocks` has min / max / all.
+  device_resident_loop   the same kernels with the scalars kept on the device (abft_cuda_[dist_]cg_solve): a path
+                         cg.cpp cannot reach, reported beside the value, not as it.
+  e2e                    a whole solve from host buffers: b, x uploaded, K iterations, x downloaded, all timed.
+  roofline               spmv_kernel alone, back to back (matrix stream >> L2), algorithmic bytes / time / peak.
+  check, rr_after        correctness beside the number: rr and sum(x) after `check.iterations` iterations from
+                         x = 0 on the same b, and rr after warm-up + K iterations; the reference arm prints the
+                         same keys (relative difference of rr <= 1e-10 is the north_star's bar).
+  workloads              BASELINE configs[3] (512^2 -b 64, sec8) and configs[4] (power-law, sec7 / constraints) at
+                         their named sizes on the same N GPUs, time-boxed.
 """
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -29,6 +43,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+CHECK_ITERS = 3     # <= the smallest warm-up: the reference arm snapshots it on its way through the warm-up
 
 
 def parse():
@@ -36,20 +51,21 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--blocks", type=int, default=10, help="timed blocks of --steps iterations each (median reported)")
     ap.add_argument("--mode", default="secded")
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--workload", default="poisson3d", choices=["poisson3d", "poisson2d_blocks", "powerlaw"],
                     help="poisson3d: grid^3 7-point (default, BASELINE configs[2]); poisson2d_blocks: 512^2 5-point x 64 "
                          "diagonal blocks (largest 5-point case the 24-bit column allows, configs[3]); powerlaw: irregular "
-                         "rows, --rows x --nnz (default N=2^23, ~2e8 nnz: configs[4] as named; round 1 measured 2^21 / 5e7)")
+                         "rows, --rows x --nnz (default N=2^23, ~1.9e8 nnz: configs[4] as named)")
     ap.add_argument("--rows", type=int, default=1 << 23, help="powerlaw: N (<= 2^24 for the ECC modes)")
     ap.add_argument("--nnz", type=int, default=200_000_000, help="powerlaw: target non-zeros after mirroring")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--all-modes", type=int, default=1, help="also time every ABFT mode briefly (N=1 only)")
+    ap.add_argument("--workloads", type=int, default=1, help="also run BASELINE configs[3] and [4] briefly (any N)")
+    ap.add_argument("--budget-s", type=float, default=240.0, help="stop adding optional sections after this much wall time")
     ap.add_argument("--cpu-iters", type=int, default=5, help="iterations of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: p2p = stores over NVLink fused into the kernels (product); nccl = all-gather/all-reduce calls (baseline)")
     return ap.parse_args()
 
 
@@ -115,14 +131,27 @@ class ClockSampler:
                 "samples_total": total, "reasons": sorted(reasons)}
 
 
+def source_hash():
+    """Identifies the kernel sources the loaded library was built from (the ncu traffic capture names the same)."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "abft-sparse-cg_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode()); h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(mode, workload, grid, world):
-    """DRAM bytes (read + write) of one spmv launch from the committed ncu capture of this workload/mode
-    (profiles/r1_spmv_dram_traffic.json), or None when there is no capture for it."""
-    path = os.path.join(ROOT, "profiles", "r1_spmv_dram_traffic.json")
+    """DRAM bytes (read + write) of one spmv launch from the committed `ncu --set full` capture of this workload and
+    mode -- only if that capture was taken on a library built from the very sources in this tree; else None."""
+    path = os.path.join(ROOT, "profiles", "r2_spmv_dram_traffic.json")
     if workload != "poisson3d" or grid != 256 or world != 1 or not os.path.exists(path):
         return None
     with open(path) as f:
         d = json.load(f)
+    if d.get("source_hash") != source_hash():
+        return None
     return d.get(mode, {}).get("traffic")
 
 
@@ -145,54 +174,114 @@ def alg_bytes(N, nnz):
     return 12 * nnz + 92 * N + 4, 12 * nnz + 20 * N + 4
 
 
+def describe(args, workload, mode, mg=None, full=None):
+    """-> (N, nnz, workload string).  `full` (the generated matrix) is needed for everything but poisson3d."""
+    if workload == "poisson3d":
+        n = args.grid
+        N = n ** 3
+        nnz = 7 * N - 6 * n * n
+        return N, nnz, f"poisson3d_{n} (3D 7-point Poisson {n}^3: N={N}, nnz={nnz}), mode {mode}, -c 0 -i K"
+    what = ("2D 5-point Poisson 512^2 replicated -b 64" if workload == "poisson2d_blocks"
+            else "power-law row lengths (Zipf 2.0, <= 4096 per row), SPD")
+    return full.N, full.nnz, f"{workload} ({what}: N={full.N}, nnz={full.nnz}), mode {mode}, -c 0 -i K"
+
+
+def generate(args, mg, workload):
+    if workload == "poisson2d_blocks":
+        return mg.poisson2d(512, 64)
+    if workload == "powerlaw":
+        return mg.powerlaw(args.rows, args.nnz, seed=1)
+    return None
+
+
+def config_of(workload_str, N, nnz, mode):
+    """Identical in both arms (the driver compares it)."""
+    return {"workload": workload_str, "mode": mode, "N": int(N), "nnz": int(nnz), "precision": "f64",
+            "l2": ("inputs larger than L2" if 12 * nnz > 2 * 126e6 else "inputs NOT larger than L2")
+                  + " (matrix stream %.0f MB per iteration)" % (12 * nnz / 1e6)}
+
+
+def rhs(N):
+    return np.random.default_rng(1).random(N)
+
+
 # ---------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU target (oracle/_ref, built from its unmodified sources)
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_run(args, t, b, iters, warm):
+def omp_threads(want=None):
+    """Set (optionally) and read back the OpenMP thread count the reference library will use."""
+    try:
+        g = ctypes.CDLL("libgomp.so.1")
+        if want:
+            g.omp_set_num_threads(int(want))
+        return int(g.omp_get_max_threads())
+    except OSError:
+        return None
+
+
+def cpu_reference_run(args, mode, t, b, iters, warm, check_iters=0):
+    """-> dict(it_s, seconds, create_s, kind, threads, check, rr_after).  The reference's CPU target driven through
+    its CGContext API from x = 0: `warm` untimed iterations, then `iters` timed ones."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the reference arm is to use the host's cores
+    ncpu = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
     import oracle_py as O
+    N = t.N
     if not os.path.exists(O.REF_SO):
-        # oracle/_ref (the reference built from its own sources) did not travel: fall back to the oracle's C port
-        # of the same algorithm -- serial, so it understates what the reference's OpenMP spmv would do
-        mode = args.mode
+        # oracle/_ref (the reference built from its own sources) did not travel: the oracle's C port of the same
+        # algorithm -- serial, so it understates what the reference's OpenMP spmv would do
         t0 = time.time()
-        om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+        om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, N)
         t_create = time.time() - t0
         L = O.lib()
-        N = t.N
         x = np.zeros(N); r = b.copy(); p = b.copy(); w = np.zeros(N)
-        rr = L.orc_dot(r, r, N)
+        st = {"rr": L.orc_dot(r, r, N)}
 
         def run(k):
-            nonlocal rr
             for _ in range(k):
                 y, fatal, ev = om.spmv(p)
                 w[:] = y
                 pw = L.orc_dot(p, w, N)
-                rr_new = L.orc_calc_xr(x, r, p, w, rr / pw, N)
-                L.orc_calc_p(p, r, rr_new / rr, N)
-                rr = rr_new
-        run(min(warm, 1))
+                rr_new = L.orc_calc_xr(x, r, p, w, st["rr"] / pw, N)
+                L.orc_calc_p(p, r, rr_new / st["rr"], N)
+                st["rr"] = rr_new
+        check = None
+        done = 0
+        if check_iters and check_iters <= warm + iters:
+            k = min(check_iters, warm)
+            run(k); done = k
+        run(warm - done)
         t0 = time.time()
         run(iters)
         dt = time.time() - t0
-        return iters / dt, dt, t_create, "port"
-    kind = "reference"
-    rc = O.RefContext(args.mode if args.mode != "crc32c" else "secded")
+        return dict(it_s=iters / dt, seconds=dt, create_s=t_create, kind="port", threads=1, check=check,
+                    rr_after={"iterations": warm + iters, "rr": st["rr"]})
+    rc = O.RefContext(mode if mode != "crc32c" else "secded")   # (the reference has no crc32c: its costliest mode stands in)
+    threads = omp_threads(ncpu)
     t0 = time.time()
-    rc.create_matrix(t.cols, t.rows, t.vals, t.N)
+    rc.create_matrix(t.cols, t.rows, t.vals, N)
     t_create = time.time() - t0
     R = rc.R
     bv = rc.vector(b); x = rc.vector(); r = rc.vector(); p = rc.vector(); w = rc.vector()
     R.ref_copy_vector(rc.ctx, r, bv)
     R.ref_copy_vector(rc.ctx, p, r)
     rr = ctypes.c_double(R.ref_dot(rc.ctx, r, r))
-    if warm:
-        R.ref_cg_iterations(rc.ctx, rc.A, x, r, p, w, warm, 0.0, ctypes.byref(rr), None)
+    done = 0
+    check = None
+
+    def run(k):
+        return R.ref_cg_iterations(rc.ctx, rc.A, x, r, p, w, k, 0.0, ctypes.byref(rr), None) if k > 0 else 0
+    if check_iters and check_iters <= warm:
+        run(check_iters); done = check_iters
+        xs = rc.view(x)
+        check = {"iterations": check_iters, "rr": rr.value, "x_sum": float(xs.sum()), "x_abs_sum": float(np.abs(xs).sum())}
+    run(warm - done)
     t0 = time.time()
-    done = R.ref_cg_iterations(rc.ctx, rc.A, x, r, p, w, iters, 0.0, ctypes.byref(rr), None)
+    got = run(iters)
     dt = time.time() - t0
-    return done / dt, dt, t_create, kind
+    return dict(it_s=got / dt, seconds=dt, create_s=t_create, kind="reference", threads=threads, check=check,
+                rr_after={"iterations": warm + got, "rr": rr.value})
 
 
 def emit(line):
@@ -204,8 +293,177 @@ def emit(line):
 _REAL_STDOUT = 1
 
 
+# ---------------------------------------------------------------------------------------------------
+# our arm: one workload on this rank's GPU (a row block of it when world > 1)
+# ---------------------------------------------------------------------------------------------------
+class Case:
+    """One (workload, mode) on `world` GPUs, driven through the C ABI the way the CGContext plugin drives it."""
+
+    def __init__(self, env, args, workload, mode, full=None):
+        self.env, self.args, self.workload, self.mode = env, args, workload, mode
+        pkg, torch, dist = env["pkg"], env["torch"], env["dist"]
+        rank, world, local_rank = env["rank"], env["world"], env["local_rank"]
+        mg = pkg.matgen
+        self.N, self.nnz, self.workload_str = describe(args, workload, mode, mg, full)
+        N = self.N
+        t_gen = time.time()
+        if full is None:
+            cuts = [(N * k) // world for k in range(world + 1)]
+            r0, r1 = cuts[rank], cuts[rank + 1]
+            t = slab_triplets(mg, args.grid, r0, r1)
+        else:
+            rowptr = full.row_pointers().astype(np.int64)
+            cuts = pkg.dist.balanced_row_cuts(rowptr, world)
+            r0, r1 = cuts[rank], cuts[rank + 1]
+            e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+            t = mg.Triplets(full.cols[e0:e1], full.rows[e0:e1], full.vals[e0:e1], N)
+        self.t_gen = time.time() - t_gen
+        self.t, self.r0, self.r1, self.nloc, self.nnz_local = t, r0, r1, r1 - r0, t.nnz
+        if world > 1:
+            counts = torch.tensor([t.nnz], dtype=torch.int64, device="cuda")
+            allc = [torch.zeros_like(counts) for _ in range(world)]
+            dist.all_gather(allc, counts)
+            nnz_offset = int(sum(int(c.item()) for c in allc[:rank]))
+        else:
+            nnz_offset = 0
+        self.ctx = ctx = pkg.CUDAContext(mode, local_rank)
+        tu = time.time()
+        self.dcg = None
+        if world > 1:
+            def all_gather_obj(obj):
+                out = [None] * world
+                dist.all_gather_object(out, obj)
+                return out
+            self.dcg = dcg = pkg.dist.DistCG(ctx, rank, world, all_gather_obj, t, cuts, N, nnz_offset)
+            self.A = dcg.A
+            self.p_full, self.p_loc, self.vb, self.x, self.r, self.w = dcg.p_full, dcg.p, dcg.b, dcg.x, dcg.r, dcg.w
+        else:
+            self.A = ctx.create_matrix_part(t.cols, t.rows, t.vals, self.nloc, N, r0, nnz_offset)
+            self.p_full = ctx.create_vector(N)
+            self.p_loc = self.p_full
+            self.vb, self.x, self.r, self.w = (ctx.create_vector(self.nloc) for _ in range(4))
+        ctx.sync()
+        self.t_upload = time.time() - tu
+        self.stream = torch.cuda.ExternalStream(ctx.L.abft_cuda_ctx_stream(ctx.ctx), device=torch.device("cuda", local_rank))
+        self.hb = ctx.map_vector(self.vb)
+        self.hb[:] = rhs(N)[r0:r1]
+        self.hx = ctx.map_vector(self.x)
+        self.hx[:] = 0.0
+        self.rr = 0.0
+        self.iterations = 0     # since the last start_solve
+
+    # ---- cg.cpp:45-118 through the plugin calls ----
+    def start_solve(self):
+        ctx = self.ctx
+        ctx.unmap_vector(self.vb, self.hb)          # H2D from the pinned map buffers
+        ctx.unmap_vector(self.x, self.hx)
+        if self.dcg:
+            self.dcg.start()
+            self.rr = self.dcg.rr
+        else:
+            ctx.copy_vector(self.r, self.vb)
+            ctx.copy_vector(self.p_loc, self.r)
+            self.rr = ctx.dot(self.r, self.r)
+        self.iterations = 0
+
+    def iterate(self, k):
+        """k iterations of the plugin path: abft_cuda_[dist_]cg_host_loop = cg.cpp's loop body over the four public
+        entry points (spmv, dot, calc_xr, calc_p; two host-visible scalars per iteration), compiled like cg.cpp is."""
+        if self.dcg:
+            self.dcg.rr = self.rr
+            self.dcg.host_loop(k, 0.0)
+            self.rr = self.dcg.rr
+        else:
+            _, self.rr = self.ctx.cg_host_loop(self.A, self.x, self.r, self.p_loc, self.w, k, 0.0, self.rr)
+        self.iterations += k
+
+    def dev_loop(self, k):
+        if self.dcg:
+            return self.dcg.solve_device(k, 0.0, k)[0]
+        return self.ctx.cg_solve_device(self.A, self.vb, self.x, self.r, self.p_loc, self.w, k, 0.0, k)[0]
+
+    def barrier(self):
+        torch, dist = self.env["torch"], self.env["dist"]
+        torch.cuda.synchronize()
+        if self.env["world"] > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn):
+        """device time of fn() on the context's stream, max over ranks (ms)"""
+        torch, dist = self.env["torch"], self.env["dist"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        fn()
+        e1.record(self.stream)
+        e1.synchronize()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if self.env["world"] > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def x_sums(self):
+        """(sum x, sum |x|) over all ranks, added in rank order."""
+        xs = self.ctx.download(self.x)
+        mine = (float(xs.sum()), float(np.abs(xs).sum()))
+        if self.env["world"] == 1:
+            return mine
+        out = [None] * self.env["world"]
+        self.env["dist"].all_gather_object(out, mine)
+        return float(sum(o[0] for o in out)), float(sum(o[1] for o in out))
+
+    def spmv_ms(self, reps):
+        ctx = self.ctx
+        # (with the fused exchange the spmv alone would wait for a push that never comes: the plain kernel is timed)
+        for _ in range(3):
+            ctx.spmv(self.A, self.p_full, self.w)
+        return self.timed(lambda: [ctx.spmv(self.A, self.p_full, self.w) for _ in range(reps)]) / reps
+
+    def close(self):
+        if self.dcg:
+            self.dcg.close()
+        self.ctx.destroy_matrix(self.A)
+        self.ctx.close()
+
+
+def brief(case, steps, peak):
+    """it/s of the plugin path, the device loop and the spmv kernel of one case (one block each)."""
+    world = case.env["world"]
+    B_alg, B_spmv = alg_bytes(case.N, case.nnz)
+    case.start_solve()
+    case.iterate(5)
+    ms_host = case.timed(lambda: case.iterate(steps)) / steps
+    rr = case.rr
+    case.ctx.report_faults()
+    case.dev_loop(5)
+    box = {}
+    ms_dev = case.timed(lambda: box.update(it=case.dev_loop(steps))) / steps
+    ms_sp = case.spmv_ms(30)
+    case.ctx.report_faults()
+    out = {"workload": case.workload_str, "it_s": 1e3 / ms_host, "ms_per_step": ms_host,
+           "iter_frac": (B_alg / world) / (ms_host * 1e-3) / 1e9 / peak,
+           "device_resident_loop_it_s": 1e3 / ms_dev,
+           "spmv_ms": ms_sp, "spmv_frac": (B_spmv / world) / (ms_sp * 1e-3) / 1e9 / peak,
+           "rr_after": {"iterations": 5 + steps, "rr": rr},
+           "nnz_per_gpu": case.nnz_local, "rows_per_gpu": case.nloc,
+           "setup": {"generate_s": case.t_gen, "create_matrix_s": case.t_upload}}
+    if case.dcg:
+        out["pushed_bytes_per_rank_per_iteration"] = case.env["pkg"].dist.exchanged_bytes(case.dcg.plan)
+    if case.workload == "powerlaw":
+        # random columns: every non-zero is one 32-byte sector request for 8 useful bytes, and the B200 serves one such
+        # request per clock per SM (tools/gather_bench.cu, profiles/r1_gather_bench.txt: 288 G/s from an L2-resident
+        # vector) -- that, not HBM, is this workload's ceiling (DESIGN.md 3.1)
+        g = case.nnz_local / (ms_sp * 1e-3) / 1e9
+        out["gather_rate"] = {"achieved": g, "peak": 288.0, "unit": "G gathers/s", "frac": g / 288.0,
+                              "peak_source": "measured: profiles/r1_gather_bench.txt (1 sector per clock per SM)"}
+    return out
+
+
 def main():
     global _REAL_STDOUT
+    t_start = time.time()
     args = parse()
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
@@ -215,255 +473,125 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         args.gpus = world
+    warm = max(args.warmup, 3)
 
     import pkg_loader
     pkg = pkg_loader.load()
     mg = pkg.matgen
-    n = args.grid
-    full = None
-    if args.workload == "poisson3d":
-        N = n ** 3
-        nnz = 7 * N - 6 * n * n
-        workload = f"poisson3d_{n} (3D 7-point Poisson {n}^3: N={N}, nnz={nnz}), mode {args.mode}, -c 0 -i K"
-    else:
-        full = mg.poisson2d(512, 64) if args.workload == "poisson2d_blocks" else mg.powerlaw(args.rows, args.nnz, seed=1)
-        N, nnz = full.N, full.nnz
-        what = ("2D 5-point Poisson 512^2 replicated -b 64" if args.workload == "poisson2d_blocks"
-                else "power-law row lengths (Zipf 2.0, <= 4096 per row), SPD")
-        workload = f"{args.workload} ({what}: N={N}, nnz={nnz}), mode {args.mode}, -c 0 -i K"
-    B_alg, B_spmv = alg_bytes(N, nnz)
     peak, peak_src = peaks()
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
-        t = slab_triplets(mg, n, 0, N) if full is None else full
-        b = np.random.default_rng(1).random(N)
-        its, dt, t_create, kind = cpu_reference_run(args, t, b, args.steps, args.warmup)
-        cores = os.cpu_count() if kind == "reference" else 1
+        full = generate(args, mg, args.workload)
+        N, nnz, workload = describe(args, args.workload, args.mode, mg, full)
+        t = slab_triplets(mg, args.grid, 0, N) if full is None else full
+        res = cpu_reference_run(args, args.mode, t, rhs(N), args.steps, warm, CHECK_ITERS)
+        its = res["it_s"]
         line = {"impl": "reference", "metric": "cg_iterations_per_sec", "value": its, "unit": "it/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / its, "higher_is_better": True,
+                "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 / its, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "threads": cores,
-                           "note": "reference cg-csr CPU target (CSR/CPUContext.cpp) through its CGContext API, "
-                                   "OpenMP over all host cores (only spmv is parallel in the reference)"},
-                "cpu_baseline": {"value": its, "unit": "it/s", "cores": cores, "kind": kind,
-                                 "sample": f"{args.steps} CG iterations on the full matrix after {args.warmup} warm-up"},
-                "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "config": config_of(workload, N, nnz, args.mode),
+                "cpu_baseline": {"value": its, "unit": "it/s", "cores": res["threads"], "kind": res["kind"],
+                                 "sample": f"{args.steps} CG iterations on the full matrix after {warm} warm-up "
+                                           f"({res['seconds']:.1f} s; create_matrix {res['create_s']:.1f} s untimed)"},
+                "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "check": res["check"], "rr_after": res["rr_after"],
+                "details": {"omp_threads": res["threads"], "host_cpus": os.cpu_count(),
+                            "note": "reference cg-csr CPU target (CSR/CPUContext.cpp) through its CGContext API, OpenMP over "
+                                    "all host cores (only spmv is parallel in the reference)"
+                                    + ("; the reference has no crc32c mode: secded stands in" if args.mode == "crc32c" else "")}}
         emit(line)
         return
 
     # ------------------------------------------------------------------ our arm
-    os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout and would precede the JSON line
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
+    env = dict(pkg=pkg, torch=torch, dist=dist, rank=rank, world=world, local_rank=local_rank)
     sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi takes a while to spin up
-    # row partition (contiguous, balanced by rows == by nnz up to the boundary planes)
-    t_gen = time.time()
-    if full is None:
-        cuts = [(N * k) // world for k in range(world + 1)]
-        r0, r1 = cuts[rank], cuts[rank + 1]
-        t = slab_triplets(mg, n, r0, r1)
-    else:
-        rowptr = full.row_pointers().astype(np.int64)
-        cuts = pkg.dist.balanced_row_cuts(rowptr, world)
-        r0, r1 = cuts[rank], cuts[rank + 1]
-        e0, e1 = int(rowptr[r0]), int(rowptr[r1])
-        t = mg.Triplets(full.cols[e0:e1], full.rows[e0:e1], full.vals[e0:e1], N)
-    t_gen = time.time() - t_gen
-    nnz_local = t.nnz
-    if world > 1:
-        counts = torch.tensor([nnz_local], dtype=torch.int64, device="cuda")
-        allc = [torch.zeros_like(counts) for _ in range(world)]
-        dist.all_gather(allc, counts)
-        nnz_offset = int(sum(int(c.item()) for c in allc[:rank]))
-    else:
-        nnz_offset = 0
-    b_full = np.random.default_rng(1).random(N)
-    nloc = r1 - r0
 
-    def setup(mode):
-        ctx = pkg.CUDAContext(mode, local_rank)
-        tu = time.time()
-        A = ctx.create_matrix_part(t.cols, t.rows, t.vals, nloc, N, r0, nnz_offset)
-        ctx.sync()
-        return ctx, A, time.time() - tu
+    full = generate(args, mg, args.workload)
+    case = Case(env, args, args.workload, args.mode, full)
+    ctx = case.ctx
+    N, nnz, workload = case.N, case.nnz, case.workload_str
+    B_alg, B_spmv = alg_bytes(N, nnz)
+    K = args.steps
 
-    use_p2p = world > 1 and args.exchange == "p2p"
-    if use_p2p:
-        def all_gather_obj(obj):
-            out = [None] * world
-            dist.all_gather_object(out, obj)
-            return out
-        ctx = pkg.CUDAContext(args.mode, local_rank)
-        tu = time.time()
-        dcg = pkg.dist.DistCG(ctx, rank, world, all_gather_obj, t, cuts, N, nnz_offset)
-        ctx.sync()
-        A, t_upload = dcg.A, time.time() - tu
-    else:
-        ctx, A, t_upload = setup(args.mode)
-    stream = torch.cuda.ExternalStream(ctx.L.abft_cuda_ctx_stream(ctx.ctx), device=torch.device("cuda", local_rank))
-
-    # vectors: p is full length on every rank (spmv gathers from it); the rest are the local slices
-    if use_p2p:
-        p_full, p_loc, vb, x, r, w = dcg.p_full, dcg.p, dcg.b, dcg.x, dcg.r, dcg.w
-        p_full_t = None
-    else:
-        p_full_t = torch.zeros(N, dtype=torch.float64, device="cuda")
-        p_full = ctx.wrap_vector(p_full_t.data_ptr(), N)
-        p_loc = ctx.view_vector(p_full, r0, nloc)
-        vb, x, r, w = (ctx.create_vector(nloc) for _ in range(4))
-    scal_t = torch.zeros(1, dtype=torch.float64, device="cuda")
-
-    def allreduce(v):
-        if world == 1:
-            return v
-        scal_t.fill_(v)
-        dist.all_reduce(scal_t)
-        return float(scal_t.item())
-
-    def exchange_p():
-        if world > 1:
-            ctx.sync()
-            dist.all_gather_into_tensor(p_full_t, p_full_t[r0:r1])
-            torch.cuda.current_stream().synchronize()
-
-    hb = ctx.map_vector(vb)
-    hb[:] = b_full[r0:r1]
-    hx = ctx.map_vector(x)
-    hx[:] = 0.0
-
-    state = {"rr": 0.0}
-
-    def start_solve():
-        ctx.unmap_vector(vb, hb)          # H2D from the pinned map buffers
-        ctx.unmap_vector(x, hx)
-        if use_p2p:
-            dcg.start()
-            state["rr"] = dcg.rr
-            return
-        ctx.copy_vector(r, vb)
-        ctx.copy_vector(p_loc, r)
-        exchange_p()
-        state["rr"] = allreduce(ctx.dot(r, r))
-
-    def iterate(k):
-        if use_p2p:
-            dcg.rr = state["rr"]
-            dcg.iterate(k, 0.0)
-            state["rr"] = dcg.rr
-            return
-        rr = state["rr"]
-        for _ in range(k):
-            ctx.spmv(A, p_full, w)
-            pw = allreduce(ctx.dot(p_loc, w))
-            alpha = rr / pw if pw != 0.0 else 0.0
-            rr_new = allreduce(ctx.calc_xr(x, r, p_loc, w, alpha))
-            beta = rr_new / rr if rr != 0.0 else 0.0
-            ctx.calc_p(p_loc, r, beta)
-            exchange_p()
-            rr = rr_new
-        state["rr"] = rr
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn):
-        """device time of fn() on the context's stream, max over ranks (ms)"""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(stream)
-        fn()
-        e1.record(stream)
-        e1.synchronize()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    # ---- host-driven loop (what the CGContext plugin does: two scalars to the host per iteration) ----
-    start_solve()
-    iterate(max(args.warmup, 3))
-    ms_host = timed(lambda: iterate(args.steps))
-    its_host = args.steps / (ms_host * 1e-3)
+    # ---- correctness beside the number: CHECK_ITERS iterations from x = 0 (the reference arm prints the same) ----
+    case.start_solve()
+    case.iterate(CHECK_ITERS)
+    xs, xa = case.x_sums()
+    check = {"iterations": CHECK_ITERS, "rr": case.rr, "x_sum": xs, "x_abs_sum": xa}
     ctx.report_faults()
 
-    # ---- value: K iterations of the device-resident loop (abft_cuda_[dist_]cg_solve: same kernels, the scalars
-    # stay on the device, one readback at the end), operands resident in HBM ----
-    if use_p2p:
-        def dev_loop(k):
-            return dcg.solve_device(k, 0.0, k)[0]
-    else:
-        if world > 1:
-            dev_loop = None          # the NCCL baseline has no device-resident loop
-        else:
-            def dev_loop(k):
-                return ctx.cg_solve_device(A, vb, x, r, p_loc, w, k, 0.0, k)[0]
-    if dev_loop is not None:
-        dev_loop(max(args.warmup, 3))
-        box = {}
+    # ---- value: the plugin path (host-driven four-call loop), --blocks blocks of K iterations ----
+    case.start_solve()
+    case.iterate(warm)
+    block_ms, rr_after = [], None
+    launches = 0
+    t_begin = time.time()
+    for blk in range(max(args.blocks, 1)):
+        if case.iterations + K > 600:       # keep rr well away from underflow: start the solve over (untimed)
+            case.start_solve()
+            case.iterate(3)
         l0 = ctx.launch_count()
-        t_begin = time.time()
-        ms_total = timed(lambda: box.update(it=dev_loop(args.steps)))
-        t_end = time.time()
+        block_ms.append(case.timed(lambda: case.iterate(K)))
         launches = ctx.launch_count() - l0
-        assert box["it"] == args.steps, box
-    else:
-        l0 = ctx.launch_count()
-        t_begin = time.time()
-        ms_total = timed(lambda: iterate(args.steps))
-        t_end = time.time()
-        launches = ctx.launch_count() - l0
+        if blk == 0:
+            rr_after = {"iterations": case.iterations, "rr": case.rr}
+    t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if sampler else None
-    its = args.steps / (ms_total * 1e-3)
+    ms_total = float(np.median(block_ms))
+    its = K / (ms_total * 1e-3)
     ctx.report_faults()
 
-    # ---- e2e: a whole solve from host buffers through the C ABI (b in, x out), K iterations ----
+    # ---- the device-resident loop (same kernels, scalars stay on the device): beside the value, not it ----
+    case.dev_loop(warm)
+    dev_ms = []
+    for _ in range(3):
+        box = {}
+        dev_ms.append(case.timed(lambda: box.update(it=case.dev_loop(K))))
+        assert box["it"] == K, box
+    ms_dev = float(np.median(dev_ms))
+    ctx.report_faults()
+
+    # ---- e2e: a whole solve from host buffers through the C ABI (b, x in; x out), K iterations ----
     def e2e():
-        start_solve()
-        iterate(args.steps)
-        ctx.map_vector(x)                 # D2H of the solution
-    ms_e2e = timed(e2e)
-    its_e2e = args.steps / (ms_e2e * 1e-3)
-    h2d = (16 * nloc) / args.steps + 16
-    d2h = (8 * nloc) / args.steps + 16
+        case.start_solve()
+        case.iterate(K)
+        ctx.map_vector(case.x)                 # D2H of the solution
+    e2e_ms = [case.timed(e2e) for _ in range(3)]
+    ms_e2e = float(np.median(e2e_ms))
+    its_e2e = K / (ms_e2e * 1e-3)
+    h2d = (16 * case.nloc) / K + 16
+    d2h = (8 * case.nloc) / K + 16
 
     # ---- roofline of the dominant kernel: spmv alone, back to back on the stream ----
-    reps = max(20, min(args.steps, 100))
-    # (with the fused exchange the spmv alone would wait for a push that never comes: time the plain kernel)
-    for _ in range(3):
-        ctx.spmv(A, p_full, w)
-    ms_spmv = timed(lambda: [ctx.spmv(A, p_full, w) for _ in range(reps)]) / reps
+    reps = max(20, min(K, 100))
+    ms_spmv = case.spmv_ms(reps)
     spmv_gbs = (B_spmv / world) / (ms_spmv * 1e-3) / 1e9
-    iter_gbs = (B_alg / world) / (ms_total / args.steps * 1e-3) / 1e9
+    iter_gbs = (B_alg / world) / (ms_total / K * 1e-3) / 1e9
     ctx.report_faults()
 
-    line = {"metric": "cg_iterations_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+    line = {"metric": "cg_iterations_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": K,
+            "warmup": warm, "ms_per_step": ms_total / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "rows_per_gpu": nloc, "nnz_per_gpu": nnz_local,
-                       "partition": "1-D contiguous row blocks" if world > 1 else "single GPU",
-                       "exchange": ("none" if world == 1 else
-                                    "fused: halo of p stored into the peers' copies over NVLink inside calc_p, "
-                                    "scalars all-reduced through peer memory inside the reductions (%d B pushed per rank per iteration)"
-                                    % pkg.dist.exchanged_bytes(dcg.plan) if use_p2p else
-                                    "NCCL all-gather of p + all-reduce of 2 scalars (baseline)"),
-                       "l2": "inputs larger than L2 (matrix stream %.0f MB per GPU per iteration)" % (12 * nnz_local / 1e6),
-                       "abi": "C ABI of include/abft_cuda.h via ctypes; value = device-resident loop "
-                              "(abft_cuda_[dist_]cg_solve), e2e / host_driven_loop = the four plugin calls per iteration"},
-            "host_driven_loop": {"value": its_host, "unit": "it/s", "ms_per_step": ms_host / args.steps,
-                                 "what": "spmv, dot, calc_xr, calc_p through the C ABI as cg.cpp drives them, operands resident"},
+            "config": config_of(workload, N, nnz, args.mode),
+            "blocks": {"n": len(block_ms), "steps_each": K, "statistic": "median",
+                       "it_s_min": K / (max(block_ms) * 1e-3), "it_s_max": K / (min(block_ms) * 1e-3),
+                       "ms_per_block": [round(m, 4) for m in block_ms]},
+            "path": "plugin: spmv, dot, calc_xr, calc_p through the C ABI of include/abft_cuda.h as cg.cpp drives them "
+                    "(two host-visible scalars per iteration), operands resident in HBM",
+            "device_resident_loop": {"value": K / (ms_dev * 1e-3), "unit": "it/s", "ms_per_step": ms_dev / K,
+                                     "what": "abft_cuda_[dist_]cg_solve: same kernels, scalars stay on the device "
+                                             "(a path cg.cpp cannot reach)"},
             "e2e": {"value": its_e2e, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "b,x uploaded from pinned host buffers + K iterations + x downloaded, all timed"},
+                    "what": "b,x uploaded from pinned host buffers + K iterations + x downloaded, all timed "
+                            "(median of 3); the copies are %.0f MB per solve whatever K is" % (24 * case.nloc / 1e6)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": f"spmv_kernel<{args.mode}>", "achieved": spmv_gbs, "peak": peak,
                          "unit": "GB/s", "frac": spmv_gbs / peak,
@@ -471,58 +599,77 @@ def main():
                          "bytes_per_launch": B_spmv // world, "ms_per_launch": ms_spmv},
             "roofline_cg_iteration": {"bound": "hbm", "bytes_per_iteration": B_alg // world, "achieved": iter_gbs,
                                       "peak": peak, "unit": "GB/s", "frac": iter_gbs / peak},
+            "check": check, "rr_after": rr_after,
             "clocks": clocks,
-            "setup": {"generate_s": t_gen, "create_matrix_s": t_upload}}
-
+            "details": {"rows_per_gpu": case.nloc, "nnz_per_gpu": case.nnz_local,
+                        "partition": "1-D contiguous row blocks" if world > 1 else "single GPU",
+                        "collective": ("none (single GPU)" if world == 1 else
+                                       "peer-memory stores over NVLink (CUDA IPC), no NCCL on the data path: halo of p stored "
+                                       "into the peers' copies inside calc_p, scalars all-reduced through peer memory inside "
+                                       "the reductions (%d B pushed per rank per iteration); NCCL only carries setup and the "
+                                       "timing barrier" % pkg.dist.exchanged_bytes(case.dcg.plan)),
+                        "source_hash": source_hash()},
+            "setup": {"generate_s": case.t_gen, "create_matrix_s": case.t_upload}}
     if args.workload == "powerlaw":
-        # random columns: every non-zero is one 32-byte sector request for 8 useful bytes, and the B200 serves one such
-        # request per clock per SM (tools/gather_bench.cu, profiles/r1_gather_bench.txt: 288 G/s from an L2-resident
-        # vector) -- that, not HBM, is this workload's ceiling
-        gathers = nnz_local / (ms_spmv * 1e-3) / 1e9
-        line["gather_rate"] = {"achieved": gathers, "peak": 288.0, "unit": "G gathers/s", "frac": gathers / 288.0,
+        g = case.nnz_local / (ms_spmv * 1e-3) / 1e9
+        line["gather_rate"] = {"achieved": g, "peak": 288.0, "unit": "G gathers/s", "frac": g / 288.0,
                                "peak_source": "measured: profiles/r1_gather_bench.txt (1 sector per clock per SM)"}
+    b_full = rhs(N)
+    t_primary = case.t
+    case.close()
+    del case
 
-    if world == 1 and rank == 0:
-        # ---- every ABFT mode, briefly ----
-        if args.all_modes:
-            modes = {}
-            for mode in pkg.MODES:
-                if mode == args.mode:
-                    modes[mode] = {"it_s": its, "iter_frac": iter_gbs / peak, "spmv_frac": spmv_gbs / peak}
-                    continue
-                c2, A2, _ = setup(mode)
-                s2 = torch.cuda.ExternalStream(c2.L.abft_cuda_ctx_stream(c2.ctx))
-                bv, xv, rv, pv, wv = (c2.create_vector(N) for _ in range(5))
-                c2.upload(bv, b_full)
-                c2.cg_solve_device(A2, bv, xv, rv, pv, wv, 5, 0.0, 5)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize(); e0.record(s2)
-                c2.cg_solve_device(A2, bv, xv, rv, pv, wv, 50, 0.0, 50)
-                e1.record(s2); e1.synchronize()
-                ms_it = e0.elapsed_time(e1) / 50
-                e0.record(s2)
-                for _ in range(30):
-                    c2.spmv(A2, pv, wv)
-                e1.record(s2); e1.synchronize()
-                ms_sp = e0.elapsed_time(e1) / 30
-                modes[mode] = {"it_s": 1e3 / ms_it, "iter_frac": B_alg / (ms_it * 1e-3) / 1e9 / peak,
-                               "spmv_frac": B_spmv / (ms_sp * 1e-3) / 1e9 / peak}
-                c2.report_faults()
-                c2.destroy_matrix(A2)
-                c2.close()
-            line["modes"] = modes
+    def over_budget():
+        flag = torch.tensor([1 if time.time() - t_start > args.budget_s else 0], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        return bool(flag.item())
 
-        # ---- CPU baseline: the reference's CPU target on this box's host cores, bounded sample ----
-        if not args.no_cpu_baseline:
+    # ---- every ABFT mode, briefly (N = 1) ----
+    if world == 1 and args.all_modes:
+        modes = {args.mode: {"it_s": its, "iter_frac": iter_gbs / peak, "spmv_frac": spmv_gbs / peak,
+                             "device_resident_loop_it_s": K / (ms_dev * 1e-3)}}
+        for mode in pkg.MODES:
+            if mode == args.mode or over_budget():
+                continue
+            c2 = Case(env, args, args.workload, mode, full)
+            r = brief(c2, 50, peak)
+            modes[mode] = {k: r[k] for k in ("it_s", "iter_frac", "spmv_frac", "device_resident_loop_it_s")}
+            c2.close()
+            del c2
+        line["modes"] = modes
+
+    # ---- BASELINE configs[3] and configs[4] at their named sizes, on the same GPUs ----
+    if args.workloads and args.workload == "poisson3d":
+        wl = {}
+        full = None
+        for name, mode in (("poisson2d_blocks", "sec8"), ("powerlaw", "sec7"), ("powerlaw", "constraints")):
+            if over_budget():
+                wl[f"{name}_{mode}"] = {"skipped": "time budget (--budget-s)"}
+                continue
             try:
-                v, dt, t_create, kind = cpu_reference_run(args, t, b_full, args.cpu_iters, 1)
-                line["cpu_baseline"] = {"value": v, "unit": "it/s", "cores": os.cpu_count() if kind == "reference" else 1,
-                                        "kind": kind,
-                                        "sample": f"{args.cpu_iters} CG iterations on the full matrix "
-                                                  f"({dt:.1f} s; create_matrix {t_create:.1f} s untimed), OpenMP all cores"}
-            except Exception as e:
-                line["cpu_baseline"] = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "unavailable",
-                                        "sample": str(e)}
+                if full is None or full_name != name:
+                    full, full_name = generate(args, mg, name), name
+                c2 = Case(env, args, name, mode, full)
+                wl[f"{name}_{mode}"] = brief(c2, min(K, 100), peak)
+                c2.close()
+                del c2
+            except Exception as e:      # an optional section must not take the headline down with it
+                wl[f"{name}_{mode}"] = {"error": repr(e)[:300]}
+        line["workloads"] = wl
+
+    # ---- CPU baseline: the reference's CPU target on this box's host cores, bounded sample ----
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        try:
+            t_all = t_primary if args.workload == "poisson3d" else generate(args, mg, args.workload)
+            res = cpu_reference_run(args, args.mode, t_all, b_full, args.cpu_iters, 1)
+            line["cpu_baseline"] = {"value": res["it_s"], "unit": "it/s", "cores": res["threads"], "kind": res["kind"],
+                                    "sample": f"{args.cpu_iters} CG iterations on the full matrix "
+                                              f"({res['seconds']:.1f} s; create_matrix {res['create_s']:.1f} s untimed), "
+                                              f"OpenMP threads = {res['threads']} of {os.cpu_count()} host CPUs"}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "it/s", "cores": os.cpu_count(), "kind": "unavailable",
+                                    "sample": str(e)}
     if rank == 0:
         emit(line)
     if world > 1:

@@ -56,9 +56,12 @@ enum abft_event_kind {
   ABFT_EV_COL_SIZE = 7,         /* "column size constraint violated at index %d"   fatal */
   ABFT_EV_COL_ORDER = 8,        /* "column order constraint violated at index %d"  fatal */
   ABFT_EV_CRC_ROW = 9,          /* "[CRC32C] error detected in row %d"             fatal */
-  /* row-pointer protection (repository-defined, opt-in build: csrc/rowsecc.cuh); index = pair of row pointers */
+  /* row-pointer protection (repository-defined: csrc/rowsecc.cuh, ABFT_CUDA_PROTECT_ROWS=secded); index = pair of row pointers */
   ABFT_EV_ROWPTR_CORRECTED = 10, /* "[ROWS] corrected bit %u of row pointer pair %d"        */
-  ABFT_EV_ROWPTR_DOUBLE = 11     /* "[ROWS] double-bit error detected in row pointer pair %d" fatal */
+  ABFT_EV_ROWPTR_DOUBLE = 11,    /* "[ROWS] double-bit error detected in row pointer pair %d" fatal */
+  /* more faults in one spmv than the device log holds (16384): the records past that were dropped, so the lines
+   * printed can no longer equal the reference's -- reported last and fatal instead of silently; index = records dropped */
+  ABFT_EV_LOG_OVERFLOW = 12      /* "fault log overflow: %d events dropped"                 fatal */
 };
 
 typedef struct abft_event {
@@ -87,6 +90,15 @@ void abft_cuda_ctx_destroy(abft_ctx *ctx);
 int abft_cuda_ctx_mode(const abft_ctx *ctx);
 int abft_cuda_ctx_sync(abft_ctx *ctx); /* wait for everything queued on the context */
 void *abft_cuda_ctx_stream(abft_ctx *ctx); /* the context's cudaStream_t */
+/* Measurement aid (off by default; a null pointer in the kernels' arguments): per CG iteration, nanosecond
+ * globaltimer stamps of where the time between the streams goes -- row i (of `rows`, a ring) holds ABFT_PHASE_SLOTS
+ * 64-bit values: 0 spmv begins, 1 spmv has seen every peer's push of p, 2 spmv's last CTA enters the cross-rank
+ * all-reduce of p.w, 3 p.w published, 4 calc_xr begins, 5 its last CTA enters the all-reduce of r.r, 6 r.r
+ * published, 7 calc_p (+ push) begins, 8 every store to the peers has landed.  globaltimer is one clock for all GPUs
+ * of a box, so rows of different ranks can be laid side by side.  rows = 0 switches it off again. */
+#define ABFT_PHASE_SLOTS 12
+int abft_cuda_phases_enable(abft_ctx *ctx, int rows);
+int abft_cuda_phases_read(abft_ctx *ctx, uint64_t *out, int cap_rows); /* -> rows copied (oldest first up to `rows`) */
 
 /* ---- matrix: create_matrix / destroy_matrix (CSR/CPUContext.cpp:11-52) ----
  * Triplets sorted by (row, col), 0-based (what cg.cpp:394-418 passes).  The
@@ -111,6 +123,10 @@ void abft_cuda_matrix_destroy(abft_ctx *ctx, abft_matrix *mat);
  * {row_begin, nnz_begin, nnz_end, info} (info: bits 0..15 rows, bit 16 thread-per-row tile, bit 17 single row longer
  * than a tile, bits 18..29 longest row) and returns the number of tiles.  Needs no device. */
 int abft_cuda_plan_tiles(const uint32_t *rowptr, int n_rows, int tile_nnz, uint32_t *out, int cap);
+/* Host-only: the decomposition AND the kernel create_matrix picks for these row pointers in this mode:
+ * *kind = 1 tiles drawn dynamically from a counter (matrices with irregular tiles), 0 tiles in static round-robin (every
+ * stencil matrix).  Same records and return value as abft_cuda_plan_tiles. */
+int abft_cuda_plan_matrix(const uint32_t *rowptr, int n_rows, int mode, uint32_t *out, int cap, int *kind);
 int abft_cuda_matrix_rows(const abft_matrix *mat);
 int abft_cuda_matrix_nnz(const abft_matrix *mat);
 /* copy the stored (encoded) CSR arrays back; any pointer may be NULL.
@@ -192,6 +208,15 @@ int abft_cuda_cg_solve(abft_ctx *ctx, abft_matrix *A, const abft_vector *b, abft
                        abft_vector *p, abft_vector *w, int max_itrs, double conv_threshold, int check_every,
                        double *rr_out);
 
+/* ---- the plugin path as one call: the loop body of cg.cpp:94-118 over abft_cuda_spmv / _dot / _calc_xr / _calc_p,
+ * scalars on the host -- what host/CUDAContext.cpp does for the unmodified driver, compiled, so that a caller in an
+ * interpreted language (tests, bench.py) times the library and not its own call overhead.  Iterates until max_itrs
+ * or rr <= conv_threshold; *rr_io carries r.r in and out; rr_hist (may be NULL, [max_itrs]) gets r.r per iteration.
+ * Returns the iterations done (>= 0) or -1.  If a fault event is pending after an spmv, the loop stops BEFORE using
+ * that result: poll the events and, unless one was fatal, call again (the interrupted iteration is redone). */
+int abft_cuda_cg_host_loop(abft_ctx *ctx, abft_matrix *A, abft_vector *x, abft_vector *r, abft_vector *p,
+                           abft_vector *w, int max_itrs, double conv_threshold, double *rr_io, double *rr_hist);
+
 /* ---- multi-GPU: row-partitioned CG with the exchange fused into the kernels ----
  * One context per GPU (one process per GPU, or several contexts in one process).  Every rank owns a
  * row block of A (abft_cuda_matrix_create_part), the matching slices of x, r, w, b, and a FULL-length
@@ -242,6 +267,11 @@ int abft_cuda_dist_calc_xr_async(abft_ctx *ctx, abft_comm *comm, abft_vector *x,
 int abft_cuda_dist_cg_solve(abft_ctx *ctx, abft_comm *comm, abft_matrix *A, const abft_vector *b, abft_vector *x,
                             abft_vector *r, abft_vector *p_local, abft_vector *p_full, abft_vector *w, int max_itrs,
                             double conv_threshold, int check_every, double *rr_out);
+/* abft_cuda_cg_host_loop over a row partition (the abft_cuda_dist_* calls above); every rank calls it in lock-step.
+ * Faults do not interrupt it (the ranks wait on each other): poll the events afterwards. */
+int abft_cuda_dist_cg_host_loop(abft_ctx *ctx, abft_comm *comm, abft_matrix *A, abft_vector *x, abft_vector *r,
+                                abft_vector *p_local, abft_vector *p_full, abft_vector *w, int max_itrs,
+                                double conv_threshold, double *rr_io, double *rr_hist);
 
 /* ---- introspection for bench.py / tests ---- */
 /* number of kernels this library has launched on the context since creation */

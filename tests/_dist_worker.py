@@ -134,6 +134,11 @@ def main():
         cg.start()
         it3 = cg.iterate(2000, 1e-10)
         dev_same.append(bool(it3 == it and np.array_equal(ctx.download(cg.x), x_host_loop)))
+        # the compiled form of that loop (abft_cuda_dist_cg_host_loop: what bench.py times): the same four calls
+        ctx.upload(cg.x, np.zeros(r1 - r0))
+        cg.start()
+        it4 = cg.host_loop(2000, 1e-10)
+        dev_same.append(bool(it4 == it and cg.rr == rr_host_loop and np.array_equal(ctx.download(cg.x), x_host_loop)))
         ctx.report_faults()
         result = dict(iterations=it, rr=rr_host_loop, x=np.concatenate(xs).tolist(), hist=hist, lines=all_lines, cuts=cuts,
                       plan=cg.plan, e0_last=e0, dev_same=all_gather(dev_same))

@@ -38,10 +38,10 @@ void spmv_mode(Emu *e, const double *vec, double *result) {
   const int grid = std::max(1, std::min((int)((e->view.N + kBlock - 1) / kBlock), 3));  // few CTAs: exercises the grid stride
   if (e->grouped) {
     run_grid(grid, kBlock, [&] { coo_spmv_kernel<MODE, true>(e->view, vec, result, L); });
-    run_grid(1, 32, [&] { coo_stray_kernel<MODE, true>(e->view, vec, result); });
+    run_grid(1, 32, [&] { coo_stray_kernel<MODE, true>(e->view, vec, result, L); });
   } else {
     run_grid(grid, kBlock, [&] { coo_spmv_kernel<MODE, false>(e->view, vec, result, L); });
-    run_grid(1, 32, [&] { coo_stray_kernel<MODE, false>(e->view, vec, result); });
+    run_grid(1, 32, [&] { coo_stray_kernel<MODE, false>(e->view, vec, result, L); });
   }
 }
 }  // namespace

@@ -20,6 +20,7 @@ struct Emu {
   std::vector<double> vals;
   std::vector<Tile> tiles;
   bool dyn = false;
+  int kind = 0;  // abft_cuda_plan_matrix: 0 static round-robin, 1 dynamic schedule
   bool rows_ecc = false;
   unsigned int tile_counter = 0;
   DevLog log;
@@ -43,10 +44,9 @@ ReduceOut reduce_of(Emu *e) {
 void fill_crc_tables() {
   for (int s = 0; s < 4; s++)
     for (uint32_t i = 0; i < 256; i++) g_crc_tab[s * 256 + i] = crc32c_table_entry(i, s);
-#if ABFT_CRC_CHUNK
-  for (int j = 0; j < kCrcChunks; j++)
-    for (uint32_t c = 0; c < (1u << crc_chunk_bits(j)); c++) g_crc_chunk_tab[crc_chunk_base(j) + c] = crc_chunk_entry(j, c);
-#endif
+  for (int m = 1; m <= kCrcMaps; m++)
+    for (int j = 0; j < kCrcChunks; j++)
+      for (uint32_t c = 0; c < 32; c++) g_crc5_tab[((m - 1) * kCrcChunks + j) * 32 + c] = crc5_entry(m, j, c);
 }
 
 template <int MODE, bool DYN>
@@ -63,13 +63,11 @@ void spmv_inst(Emu *e, const double *vec, double *result) {
   A.n_cols = e->n_cols;
   A.row_offset = e->row_offset;
   A.nnz_offset = e->nnz_offset;
-#if ABFT_ROWS_ECC
   A.rows_ecc = e->rows_ecc ? 1u : 0u;
-#endif
   LogRef L{&e->log, &e->flag};
   const ReduceOut red = reduce_of(e);
   const int grid = std::max(1, std::min((int)e->tiles.size(), e->grid));
-  emu::launch(grid, kBlock, [&] { spmv_kernel<MODE, DYN>(A, vec, result, L, red, nullptr, WaitSpec{nullptr, 0u, 0u}); });
+  emu::launch(grid, SpmvCfg<DYN>::block, [&] { spmv_kernel<MODE, DYN>(A, vec, result, L, red, nullptr, WaitSpec{nullptr, 0u, 0u}); });
 }
 
 template <int MODE>
@@ -82,10 +80,7 @@ void spmv_mode(Emu *e, const double *vec, double *result) {
 extern "C" {
 
 int emu_tile_nnz(int dyn) { return dyn ? kTileNnzDyn : kTileNnz; }
-int emu_walk_uniform(void) { return ABFT_WALK_UNIFORM; }
-int emu_crc_chunk(void) { return ABFT_CRC_CHUNK; }
-int emu_crc_walk(void) { return ABFT_CRC_WALK; }
-int emu_last_refill(void) { return ABFT_SPMV_LASTREFILL; }
+int emu_spmv_block(int dyn) { return dyn ? SpmvCfg<true>::block : SpmvCfg<false>::block; }
 
 // create_matrix as abft_cuda_matrix_create_part does it: row pointers and check bits by the device kernels
 // a row partition, as abft_cuda_matrix_create_part takes it: n_rows local rows starting at global row row_offset,
@@ -130,26 +125,22 @@ void emu_destroy(void *h) {
 }
 
 // the work decomposition (from abft_cuda_plan_tiles of the real library: host logic, no device needed)
-void emu_set_tiles(void *h, const uint32_t *recs, int n_tiles, int dyn, int grid) {
+void emu_set_tiles(void *h, const uint32_t *recs, int n_tiles, int kind, int grid) {
   Emu *e = (Emu *)h;
   e->tiles.resize((size_t)n_tiles);
   for (int i = 0; i < n_tiles; i++) e->tiles[i] = Tile{recs[4 * i], recs[4 * i + 1], recs[4 * i + 2], recs[4 * i + 3]};
-  e->dyn = dyn != 0;
+  e->kind = kind;
+  e->dyn = kind == 1;
   e->grid = grid;
 }
 
-// row-pointer protection (rowsecc.cuh), as abft_cuda_matrix_create_part applies it; 0 if not compiled in
+// row-pointer protection (rowsecc.cuh), as abft_cuda_matrix_create_part applies it
 int emu_protect_rows(void *h) {
-#if ABFT_ROWS_ECC
   Emu *e = (Emu *)h;
   const uint32_t n_words = (e->n_rows + 1u + 1u) & ~1u;
   emu::launch(2, kBlock, [&] { encode_rowptr_pairs_kernel(e->rowptr.data(), n_words); });
   e->rows_ecc = true;
   return 1;
-#else
-  (void)h;
-  return 0;
-#endif
 }
 
 uint32_t *emu_cols(void *h) { return ((Emu *)h)->cols.data(); }

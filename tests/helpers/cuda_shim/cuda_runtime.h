@@ -38,6 +38,8 @@ static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {
 }
 static inline double __dadd_rn(double a, double b) { return a + b; }   // built with -ffp-contract=off
 static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline long long __double_as_longlong(double v) { long long b; memcpy(&b, &v, 8); return b; }
+static inline double __longlong_as_double(long long b) { double v; memcpy(&v, &b, 8); return v; }
 static inline int __double2loint(double v) { uint64_t b; memcpy(&b, &v, 8); return (int)(uint32_t)b; }
 static inline int __double2hiint(double v) { uint64_t b; memcpy(&b, &v, 8); return (int)(uint32_t)(b >> 32); }
 static inline double __hiloint2double(int hi, int lo) {
@@ -48,6 +50,7 @@ template <class T> static inline T atomicAdd(T *p, T v) { T old = *p; *p = old +
 template <class T> static inline T __ldcs(const T *p) { return *p; }
 template <class T> static inline T __ldcg(const T *p) { return *p; }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline void __syncthreads() {}
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}

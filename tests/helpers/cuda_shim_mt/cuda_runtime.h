@@ -24,6 +24,7 @@
 #define __device__
 #define __global__
 #define __host__
+#define __constant__
 #define __forceinline__ inline
 #define __noinline__
 #define __shared__ static
@@ -46,12 +47,22 @@ static inline uint32_t __brev(uint32_t x) {
   for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);
   return r;
 }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+// PRMT: result byte k = byte (selector nibble k) of the 8-byte pool {x (bytes 0..3), y (bytes 4..7)} (no sign modes used)
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+  const uint64_t pool = ((uint64_t)y << 32) | x;
+  uint32_t r = 0;
+  for (int k = 0; k < 4; k++) r |= (uint32_t)((pool >> (8 * ((s >> (4 * k)) & 7u))) & 0xFFu) << (8 * k);
+  return r;
+}
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline double __dadd_rn(double a, double b) { return a + b; }   // built with -ffp-contract=off
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline long long __double_as_longlong(double v) { long long b; memcpy(&b, &v, 8); return b; }
+static inline double __longlong_as_double(long long b) { double v; memcpy(&v, &b, 8); return v; }
 static inline int __double2loint(double v) { uint64_t b; memcpy(&b, &v, 8); return (int)(uint32_t)b; }
 static inline int __double2hiint(double v) { uint64_t b; memcpy(&b, &v, 8); return (int)(uint32_t)(b >> 32); }
 static inline double __hiloint2double(int hi, int lo) {

@@ -22,4 +22,33 @@ uint32_t ecc_flipped_bit(uint32_t syndrome) { return flipped_bit(syndrome); }
 uint32_t ecc_encode_column(int mode, uint32_t w0, uint32_t w1, uint32_t col) { return encode_column(mode, w0, w1, col); }
 uint32_t ecc_hamming_mask(int p, int word) { return hamming_mask(p, word); }
 
+// CRC-32C from the very table constructors the library fills its device tables with (abft_cuda.cu, ensure_tables):
+// byte-wise with the slice-0 table (create_matrix's tables) ...
+uint32_t ecc_crc32c_bytes(const uint8_t *data, int n) {
+  uint32_t c = 0xFFFFFFFFu;
+  for (int i = 0; i < n; i++) c = (c >> 8) ^ crc32c_table_entry((c ^ data[i]) & 0xFFu, 0);
+  return c ^ 0xFFFFFFFFu;
+}
+// ... slicing-by-4 with tables 0..3, one little-endian word at a time (crc_word of spmv.cuh) ...
+uint32_t ecc_crc32c_words_by4(const uint32_t *w, int n_words) {
+  uint32_t c = 0xFFFFFFFFu;
+  for (int i = 0; i < n_words; i++) {
+    const uint32_t x = c ^ w[i];
+    c = crc32c_table_entry(x & 0xFF, 3) ^ crc32c_table_entry((x >> 8) & 0xFF, 2) ^ crc32c_table_entry((x >> 16) & 0xFF, 1) ^
+        crc32c_table_entry(x >> 24, 0);
+  }
+  return c ^ 0xFFFFFFFFu;
+}
+// ... and three words at a time with the 5-bit chunk tables of F, F.F, F.F.F (crc_element of spmv.cuh: the spmv check)
+static uint32_t map5(int m, uint32_t x) {
+  uint32_t r = 0;
+  for (int j = 0; j < kCrcChunks; j++) r ^= crc5_entry(m, j, (x >> (5 * j)) & 31u);
+  return r;
+}
+uint32_t ecc_crc32c_words_by_maps(const uint32_t *w, int n_words) {   // n_words a multiple of 3
+  uint32_t c = 0xFFFFFFFFu;
+  for (int i = 0; i + 2 < n_words; i += 3) c = map5(3, c ^ w[i]) ^ map5(2, w[i + 1]) ^ map5(1, w[i + 2]);
+  return c ^ 0xFFFFFFFFu;
+}
+
 }  // extern "C"

@@ -7,7 +7,6 @@ helpers are a small state machine + memcpy) and compared with the oracle, which 
 decomposition comes from the real library's abft_cuda_plan_tiles (host logic).  Same bars as tests/test_gpu_parity.py.
 What this cannot see: memory ordering on the device, TMA alignment rules, launch configuration, performance.
 
-The shipped configuration is run in full; the opt-in ABFT_WALK_UNIFORM variant on the tiles it changes.
 """
 import ctypes as C
 import importlib.util
@@ -62,16 +61,7 @@ def _build(tmp, name, flags):
 
 @pytest.fixture(scope="module")
 def EMU(tmp_path_factory):
-    L = _build(tmp_path_factory.mktemp("csr_emu"), "shipped", [])
-    assert L.emu_walk_uniform() == 0
-    return L
-
-
-@pytest.fixture(scope="module")
-def EMU_UNIFORM(tmp_path_factory):
-    L = _build(tmp_path_factory.mktemp("csr_emu_u"), "walk_uniform", ["-DABFT_WALK_UNIFORM=1"])
-    assert L.emu_walk_uniform() == 1
-    return L
+    return _build(tmp_path_factory.mktemp("csr_emu"), "shipped", [])
 
 
 class EmuMatrix:
@@ -95,18 +85,17 @@ class EmuMatrix:
         rowptr = self.rowptr.copy()
         t = type("Part", (), {"N": n_rows})           # (below: the local row count)
 
-        def plan(tile_nnz):
-            n = lib.abft_cuda_plan_tiles(rowptr.ctypes.data, t.N, tile_nnz, None, 0)
-            out = np.zeros((max(n, 1), 4), dtype=np.uint32)
-            assert lib.abft_cuda_plan_tiles(rowptr.ctypes.data, t.N, tile_nnz, out.ctypes.data, n) == n
-            return out[:n]
-        tiles = plan(L.emu_tile_nnz(0))
-        self.dyn = bool(np.any((tiles[:, 3] & REGULAR) == 0)) and mode != "crc32c" if len(tiles) else False
-        if self.dyn:
-            tiles = plan(L.emu_tile_nnz(1))
+        # the decomposition and the kernel (static round-robin or dynamic schedule), as create_matrix picks them
+        kind = C.c_int(0)
+        n = lib.abft_cuda_plan_matrix(rowptr.ctypes.data, t.N, MODES.index(mode), None, 0, C.byref(kind))
+        tiles = np.zeros((max(n, 1), 4), dtype=np.uint32)
+        assert lib.abft_cuda_plan_matrix(rowptr.ctypes.data, t.N, MODES.index(mode), tiles.ctypes.data, n, C.byref(kind)) == n
+        tiles = tiles[:n]
+        self.kind = kind.value
+        self.dyn = self.kind == 1
         self.tiles = tiles
         L.emu_set_tiles(self.h, np.ascontiguousarray(tiles.reshape(-1)) if len(tiles) else np.zeros(4, np.uint32),
-                        len(tiles), int(self.dyn), grid)
+                        len(tiles), self.kind, grid)
 
     @property
     def cols(self):
@@ -338,14 +327,14 @@ def test_vector_kernels(EMU, pkg, O, N):
 
 
 @pytest.mark.parametrize("mode", ["none", "constraints", "sec7", "secded"])
-def test_walk_uniform_variant(EMU_UNIFORM, pkg, O, mode):
-    """-DABFT_WALK_UNIFORM=1 only changes the unrolled walk of regular tiles (rows of up to 7 elements): clean results
-    bit for bit on stencils (full warps take the unpredicated adds) and on ragged / short rows (mixed warps must not),
-    and the same events and repairs under faults."""
+def test_uniform_walk_of_full_warps(EMU, pkg, O, mode):
+    """The unrolled walk of regular tiles (rows of up to 7 elements) drops the predicate on its adds when every row of the
+    warp fills it: clean results bit for bit on stencils (full warps take the unpredicated adds) and on ragged / short
+    rows (mixed warps must not), and the same events and repairs under faults."""
     rng = np.random.default_rng(21)
     for name in ("p3d_12", "p2d_40", "p2d_12_b3", "ragged", "short_rows", "one_by_one"):
         t = shapes(pkg.matgen)[name]()
-        em = EmuMatrix(EMU_UNIFORM, pkg, mode, t)
+        em = EmuMatrix(EMU, pkg, mode, t)
         om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
         vec = rng.standard_normal(t.N)
         y, fatal, events, _ = em.spmv(vec)
@@ -363,14 +352,12 @@ def test_walk_uniform_variant(EMU_UNIFORM, pkg, O, mode):
         em.close()
 
 
-@pytest.mark.parametrize("chunk,walk", [(5, 0), (6, 1)] + ([(6, 0), (0, 1), (5, 1)] if SLOW else []))
-def test_crc_chunk_table_variant(tmp_path_factory, pkg, O, chunk, walk):
-    """-DABFT_CRC_CHUNK=5|6 (per-lane, bank-conflict-free CRC tables in the spmv check) and -DABFT_CRC_WALK=1 (the unrolled
-    CRC row walk of regular tiles): the same verdicts as the shipped loop over byte tables -- clean matrices pass (rows of >= 4 elements carry the CRC, shorter ones the SECDED byte), every single
-    and double flip in a CRC-protected row is caught, in regular tiles and in rows longer than a tile."""
-    L = _build(tmp_path_factory.mktemp(f"csr_emu_crc{chunk}{walk}"), f"crc{chunk}{walk}",
-               [f"-DABFT_CRC_CHUNK={chunk}", f"-DABFT_CRC_WALK={walk}"])
-    assert L.emu_crc_chunk() == chunk and L.emu_crc_walk() == walk
+def test_crc_row_walk(EMU, pkg, O):
+    """The spmv's CRC32C check (5-bit chunk tables of the three linear maps F, F.F, F.F.F, one entry per bank; unrolled row
+    walk on regular tiles, the one-by-one loop elsewhere) against the oracle's byte-wise CRC: clean matrices pass (rows of
+    >= 4 elements carry the CRC, shorter ones the SECDED byte), every single and double flip in a CRC-protected row is
+    caught, in regular tiles and in rows longer than a tile."""
+    L, chunk = EMU, 0
     rng = np.random.default_rng(31 + chunk)
     for name in ("p3d_12", "p2d_40", "ragged", "short_rows", "long_rows", "powerlaw"):
         t = shapes(pkg.matgen)[name]()
@@ -428,43 +415,6 @@ def test_cg_trajectory_with_the_emulated_kernels(EMU, pkg, O):
     assert np.max(np.abs(np.array(hist) - ref["rr_hist"]) / ref["rr_hist"]) <= 1e-10
     assert np.max(np.abs(x - ref["x"])) <= 1e-9 * np.max(np.abs(ref["x"]))
     em.close()
-
-
-@pytest.mark.parametrize("mode", ["none", "secded", "crc32c"])
-def test_last_refill_variant(tmp_path_factory, pkg, O, mode):
-    """-DABFT_SPMV_LASTREFILL=1 (static kernel without the per-tile CTA barrier: the warp that leaves a stage last refills
-    it): many tiles per CTA so that the stage ring turns over several times and warps drift apart; clean results bit for
-    bit, faults reported and repaired as before, rows longer than a tile (block-wide reductions in between) included."""
-    L = _build(tmp_path_factory.mktemp("csr_emu_lr"), "lastrefill", ["-DABFT_SPMV_LASTREFILL=1"])
-    assert L.emu_last_refill() == 1
-    rng = np.random.default_rng(41)
-    cases = {"p3d_16": pkg.matgen.poisson3d(16), "p2d_40": shapes(pkg.matgen)["p2d_40"](), "one": shapes(pkg.matgen)["one_by_one"]()}
-    if mode == "crc32c":
-        cases["long_rows"] = shapes(pkg.matgen)["long_rows"]()      # (static kernel in every case for this mode)
-    for name, t in cases.items():
-        for grid in (1, 3):
-            em = EmuMatrix(L, pkg, mode, t, grid=grid)
-            assert not em.dyn
-            om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
-            vec = rng.standard_normal(t.N)
-            y, fatal, events, dot = em.spmv(vec)
-            y0, _, _ = om.spmv(vec)
-            lens = np.bincount(t.rows, minlength=t.N)
-            assert not fatal and events == [], (name, grid, events)
-            assert np.array_equal(y[lens <= 32].view(np.uint64), y0[lens <= 32].view(np.uint64)), (name, grid)
-            assert abs(dot - float(np.dot(vec, y))) <= 1e-10 * max(np.abs(vec * y).sum(), 1e-300)
-            if mode != "none" and t.nnz > 10:
-                for trial in range(3):
-                    index, bit = int(rng.integers(0, t.nnz)), int(rng.integers(0, 96))
-                    em.flip(index, bit)
-                    om.flip(index, bit)
-                    y, fatal, events, _ = em.spmv(vec)
-                    y0, fatal0, ev0 = om.spmv(vec)
-                    assert (fatal, events) == (fatal0, ev0), (name, grid, index, bit)
-                    if fatal:
-                        break
-                    assert np.array_equal(em.cols, om.cols), (name, grid, index, bit)
-            em.close()
 
 
 @pytest.mark.parametrize("mode", ["constraints", "sec7", "secded", "crc32c"])

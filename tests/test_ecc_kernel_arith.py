@@ -50,3 +50,54 @@ def test_kernel_ecc_arithmetic_equals_the_oracle(E, O):
     for pos in range(1, 128):
         s = sum(((pos >> (p - 1)) & 1) << (32 - p) for p in range(1, 8))
         assert E.ecc_flipped_bit(s) == L.orc_ecc_get_flipped_bit_col8(s), pos
+
+
+def test_crc32c_published_vectors(E, O):
+    """RFC 3720 appendix B.4 (tests/golden/crc32c_rfc3720.json): the oracle's CRC and the three table forms the device
+    tables are built from (byte table, slicing-by-4, the 5-bit chunk tables of F / F.F / F.F.F the spmv check uses)
+    all reproduce the published CRC-32C values."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "crc32c_rfc3720.json")) as f:
+        G = json.load(f)
+    u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+    u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+    E.ecc_crc32c_bytes.restype = C.c_uint32
+    E.ecc_crc32c_bytes.argtypes = [u8p, C.c_int]
+    for f_ in (E.ecc_crc32c_words_by4, E.ecc_crc32c_words_by_maps):
+        f_.restype = C.c_uint32
+        f_.argtypes = [u32p, C.c_int]
+    seen_maps = 0
+    for name, v in G["vectors"].items():
+        data = bytes.fromhex(v["bytes"])
+        want = int(v["crc32c"], 16)
+        assert O.lib().orc_crc32c(data, len(data)) == want, name
+        arr = np.frombuffer(data, dtype=np.uint8).copy()
+        assert E.ecc_crc32c_bytes(arr, len(data)) == want, name
+        if len(data) % 4 == 0:
+            words = arr.view("<u4").copy()
+            assert E.ecc_crc32c_words_by4(words, len(words)) == want, name
+            if len(words) % 3 == 0:
+                assert E.ecc_crc32c_words_by_maps(words, len(words)) == want, name
+                seen_maps += 1
+    assert seen_maps >= 1     # the 48-byte PDU: four 96-bit elements
+    # random messages: the three table forms agree with the oracle
+    rng = np.random.default_rng(9)
+    for n_words in (3, 6, 21, 300):
+        words = rng.integers(0, 2**32, n_words, dtype=np.uint64).astype(np.uint32)
+        want = O.lib().orc_crc32c(words.tobytes(), 4 * n_words)
+        assert E.ecc_crc32c_words_by4(words, n_words) == want == E.ecc_crc32c_words_by_maps(words, n_words)
+        assert E.ecc_crc32c_bytes(words.view(np.uint8).copy(), 4 * n_words) == want
+
+
+def test_crc32c_row_known_answer_oracle(O, pkg):
+    """The RFC's 48-byte PDU is four 12-byte elements: a one-row crc32c matrix built from it carries the published CRC
+    in the top bytes of its four column words (the row format of DESIGN.md 5, pinned to a published vector)."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "crc32c_rfc3720.json")) as f:
+        K = json.load(f)["row_known_answer"]
+    vals = np.array([np.frombuffer(bytes.fromhex(h), dtype="<f8")[0] for h in K["values_hex"]])
+    cols = np.array(K["columns"], dtype=np.uint32)
+    N = int(cols.max()) + 1
+    om = O.OracleMatrix("crc32c", cols, np.zeros(4, np.uint32), vals, N)
+    assert [int(c >> 24) for c in om.cols] == K["crc_bytes_in_column_top_bytes"]
+    assert [int(c & 0xFFFFFF) for c in om.cols] == K["columns"]

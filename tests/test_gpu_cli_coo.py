@@ -26,6 +26,11 @@ def field(text, prefix):
     return None
 
 
+def rr_lines(text):
+    """rr of every `iteration %5d :  rr = %12.4lf` line (cg.cpp:116)."""
+    return [float(ln.split("=")[1]) for ln in text.splitlines() if ln.startswith("iteration") and "rr =" in ln]
+
+
 @pytest.fixture(scope="module")
 def exe():
     if not os.path.exists(EXE):
@@ -71,4 +76,14 @@ def test_cpu_and_cuda_agree_under_random_seeds(O, exe, mtx32):
             args = ["-f", mtx32, "-b", "4", "-c", "1e-10", "-i", "400", "-m", mode] + extra
             c1, t1 = O.run_cg_csr(exe, args + ["-t", "cuda"], fake_time=seed)
             c0, t0 = O.run_cg_csr(exe, args + ["-t", "cpu"], fake_time=seed)
-            assert (c1, faults(t1), field(t1, "ran for")) == (c0, faults(t0), field(t0, "ran for")), (mode, extra, seed)
+            assert (c1, faults(t1)) == (c0, faults(t0)), (mode, extra, seed)
+            if mode == "none":
+                # nothing detects the flip: the solve goes on with a corrupted (possibly indefinite) matrix.  Seed 3001
+                # flips exponent bit 123 of a diagonal entry (4.0 -> 5e39): after one iteration r_j = r_j - rr/p_j, and
+                # the next search direction p_j = r_j + beta p_j cancels to ~1e-12 of its terms -- the 1e-16 difference of
+                # a reordered reduction decides whether rr is 1e36 or 1e6 from then on (-t cpu runs 400 iterations,
+                # -t cuda "converges" after 388).  Only the first residual is comparable.
+                r1, r0 = rr_lines(t1)[:1], rr_lines(t0)[:1]
+                assert len(r1) == len(r0) == 1 and abs(r1[0] - r0[0]) <= 1e-9 * abs(r0[0]), (seed, r1, r0)
+            else:
+                assert field(t1, "ran for") == field(t0, "ran for"), (mode, extra, seed)

@@ -1,7 +1,8 @@
 """COO format on the GPU (abft_cuda_coo_*) against the pinned COO oracle (oracle/coo_oracle.c).
 
-All 22 green on a B200 (gpurun_out/pytest_coo*.txt, end of round 1); the same cases also run on the CPU against the
-kernels' own source through a shim of the CUDA built-ins (tests/test_coo_kernel_logic.py).
+Every test runs in both element layouts (coo.cuh): the default grouped one and the caller-order one
+(ABFT_CUDA_COO_LAYOUT=caller).  The same cases also run on the CPU against the kernels' own source through a shim of
+the CUDA built-ins (tests/test_coo_kernel_logic.py).
 
 Bars: bit-exact encoded elements, events (kind, index, bit), repaired elements and result[] (the kernel keeps the
 reference's accumulation order per output entry and uses no FMA); CG iteration counts equal, rr within 1e-10
@@ -17,6 +18,15 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-10
 MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded"]
+
+
+@pytest.fixture(params=["grouped", "caller"], autouse=True)
+def layout(request, monkeypatch):
+    if request.param == "caller":
+        monkeypatch.setenv("ABFT_CUDA_COO_LAYOUT", "caller")
+    else:
+        monkeypatch.delenv("ABFT_CUDA_COO_LAYOUT", raising=False)
+    return request.param
 
 
 @pytest.fixture(scope="module")

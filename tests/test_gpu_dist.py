@@ -18,7 +18,7 @@ def n_gpus():
 @pytest.mark.parametrize("shape,mode", [("p2d", "secded"), ("p3d", "none"), ("blocks", "sec7"), ("powerlaw", "constraints"),
                                         ("p3d", "crc32c")])
 def test_dist_cg_matches_oracle(pkg, O, tmp_path, shape, mode):
-    world = min(n_gpus(), 4)
+    world = min(n_gpus(), 8)       # every GPU of the box (the exchange windows hold up to 8 ranks)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     import importlib.util, os
@@ -43,7 +43,7 @@ def test_dist_cg_matches_oracle(pkg, O, tmp_path, shape, mode):
 
 
 def test_dist_fault_reports_global_index(pkg, O, tmp_path):
-    world = min(n_gpus(), 4)
+    world = min(n_gpus(), 8)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     res = run_worker(world, "gpu", "p2d", tmp_path, extra=["secded", "flip"])

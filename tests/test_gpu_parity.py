@@ -627,3 +627,93 @@ def test_all_double_flips_match_oracle(pkg, O, mode):
         assert np.array_equal(cols, om.cols) and np.array_equal(vals.view(np.uint64), om.values.view(np.uint64))
         assert np.array_equal(y, y0, equal_nan=True)      # (a flipped exponent can make a NaN: payloads may differ)
         ctx.close()
+
+
+def test_fault_log_overflow_is_reported_not_dropped(pkg):
+    """More faults in one spmv than the device log holds (16384 records): every element is still repaired, the records
+    that fit come back in order, and the last one says how many were dropped -- fatal, because the printed lines can no
+    longer equal the reference's (which has no such limit).  Polling hands the events out in pages."""
+    n, faults = 20000, 17000
+    rng = np.random.default_rng(5)
+    t = pkg.matgen.Triplets(np.arange(n), np.arange(n), rng.standard_normal(n), n)
+    ctx = pkg.CUDAContext("sec7")
+    A = ctx.create_matrix(t.cols, t.rows, t.vals, t.N)
+    clean_cols, _, clean_vals = ctx.read_matrix(A)
+    bits = rng.integers(0, 64, faults)
+    for i in range(faults):
+        ctx.flip_bit(A, i, int(bits[i]))
+    v, w = ctx.create_vector(n), ctx.create_vector(n)
+    ctx.upload(v, np.ones(n))
+    ctx.spmv(A, v, w)
+    events, fatal = ctx.poll_events(cap=1000)
+    assert fatal and len(events) == 16384 + 1
+    assert events[-1] == (12, faults - 16384, 0)
+    assert ctx.format_event(events[-1]) == f"fault log overflow: {faults - 16384} events dropped"
+    idx = [e[1] for e in events[:-1]]
+    assert idx == sorted(set(idx)) and all(e[0] == 2 and e[2] == bits[e[1]] for e in events[:-1])
+    cols, _, vals = ctx.read_matrix(A)
+    assert np.array_equal(cols, clean_cols) and np.array_equal(vals.view(np.uint64), clean_vals.view(np.uint64))
+    ctx.spmv(A, v, w)
+    assert ctx.poll_events() == ([], False)
+    ctx.close()
+
+
+def test_crc32c_row_known_answer_on_device(pkg):
+    """RFC 3720 B.4's 48-byte PDU as a one-row crc32c matrix (tests/golden/crc32c_rfc3720.json): the device-side encode
+    writes the PUBLISHED CRC-32C into the top bytes of the four column words, and the spmv check (different tables:
+    5-bit chunks of the three linear maps) accepts the row; one flipped bit anywhere in the 48 bytes is caught."""
+    from conftest import load_golden
+    K = load_golden("crc32c_rfc3720.json")["row_known_answer"]
+    vals = np.array([np.frombuffer(bytes.fromhex(h), dtype="<f8")[0] for h in K["values_hex"]])
+    cols = np.array(K["columns"], dtype=np.uint32)
+    N = int(cols.max()) + 1
+    ctx = pkg.CUDAContext("crc32c")
+    A = ctx.create_matrix(cols, np.zeros(4, np.uint32), vals, N)
+    got, _, _ = ctx.read_matrix(A)
+    assert [int(c >> 24) for c in got] == K["crc_bytes_in_column_top_bytes"]
+    v, w = ctx.create_vector(N), ctx.create_vector(N)
+    ctx.upload(v, np.ones(N))
+    ctx.spmv(A, v, w)
+    assert ctx.poll_events() == ([], False)
+    for index, bit in [(0, 0), (1, 37), (2, 63), (3, 64), (2, 87)]:
+        ctx.flip_bit(A, index, bit)
+        ctx.spmv(A, v, w)
+        events, fatal = ctx.poll_events()
+        assert fatal and events == [(9, 0, 0)], (index, bit, events)
+        ctx.flip_bit(A, index, bit)
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["none", "secded"])
+def test_compiled_host_loop_equals_the_four_calls(pkg, O, mode):
+    """abft_cuda_cg_host_loop (what bench.py times as the plugin path) is the loop of cg.cpp:94-118 over the same four
+    entry points as CUDAContext.cg(): same iteration count, same residual history and solution, bit for bit -- also
+    with a fault repaired on the way (the loop stops before using that spmv's result, the fault is reported, and the
+    iteration is redone)."""
+    t = pkg.matgen.poisson2d(48)
+    b = pkg.matgen.rhs(t.N)
+    runs = []
+    for compiled in (False, True):
+        ctx = pkg.CUDAContext(mode)
+        A = ctx.create_matrix(t.cols, t.rows, t.vals, t.N)
+        if mode == "secded":
+            ctx.flip_bit(A, 777, 41)
+        vb, x, r, p, w = (ctx.create_vector(t.N) for _ in range(5))
+        ctx.upload(vb, b)
+        if compiled:
+            ctx.copy_vector(r, vb)
+            ctx.copy_vector(p, r)
+            hist = []
+            it, rr = ctx.cg_host_loop(A, x, r, p, w, 1000, 1e-10, ctx.dot(r, r), hist)
+            hist = np.asarray(hist)
+        else:
+            it, hist = ctx.cg(A, vb, x, r, p, w, 1000, 1e-10)
+        runs.append((it, hist, ctx.download(x), list(ctx.messages)))
+        ctx.close()
+    assert runs[0][0] == runs[1][0] and np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+    assert runs[0][3] == runs[1][3] == (["[ECC] corrected bit 41 at index 777"] if mode == "secded" else [])
+    ref = O.OracleMatrix(mode, t.cols, t.rows, t.vals, t.N)
+    if mode == "secded":
+        ref.flip(777, 41)
+    want = ref.cg(b, 1000, 1e-10)
+    assert runs[1][0] == want["iterations"] and np.max(np.abs(runs[1][1] - want["rr_hist"]) / want["rr_hist"]) <= RTOL

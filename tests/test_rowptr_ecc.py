@@ -1,6 +1,6 @@
 """Row-pointer protection (scope row f.2; repository-defined, PARITY UNPINNED -- the reference trusts rows[]):
 the device code of csrc/rowsecc.cuh, compiled for the host and run through the CSR kernel emulator
-(tests/helpers/cuda_shim_mt/, built with -DABFT_ROWS_ECC=1), against the independent bit-by-bit restatement in
+(tests/helpers/cuda_shim_mt/), against the independent bit-by-bit restatement in
 oracle/rowptr_ecc.c.  Opt-in at compile time until it has run on a GPU (tools/ab_variants.sh carries `rowsecc`)."""
 import ctypes as C
 import os
@@ -26,7 +26,7 @@ def RO(O):
 
 @pytest.fixture(scope="module")
 def EMU_ROWS(tmp_path_factory):
-    L = _build(tmp_path_factory.mktemp("csr_emu_rows"), "rowsecc", ["-DABFT_ROWS_ECC=1"])
+    L = _build(tmp_path_factory.mktemp("csr_emu_rows"), "rowsecc", [])
     L.emu_protect_rows.restype = C.c_int
     L.emu_protect_rows.argtypes = [C.c_void_p]
     return L

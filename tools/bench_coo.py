@@ -31,10 +31,10 @@ def main():
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--layout", default="caller", choices=["caller", "grouped"])
+    ap.add_argument("--layout", default="grouped", choices=["caller", "grouped"])
     a = ap.parse_args()
-    if a.layout == "grouped":
-        os.environ["ABFT_CUDA_COO_LAYOUT"] = "grouped"
+    if a.layout == "caller":
+        os.environ["ABFT_CUDA_COO_LAYOUT"] = "caller"
     else:
         os.environ.pop("ABFT_CUDA_COO_LAYOUT", None)
     import torch
