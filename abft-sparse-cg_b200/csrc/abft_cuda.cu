@@ -77,8 +77,6 @@ struct abft_ctx {
   unsigned int *h_flag = nullptr;   // mapped pinned
   double *d_scalars = nullptr;      // kNumSlots
   double *h_scalars = nullptr;      // mapped pinned mirror
-  unsigned int *h_seq = nullptr;    // mapped pinned: sequence number of the value in h_scalars[slot] (the host polls it)
-  unsigned int seq_issued[kNumSlots] = {};  // last sequence number handed to a reduction into each slot
   double *d_partials = nullptr;     // kMaxPartials
   unsigned int *d_counter = nullptr;
   int *d_loop = nullptr;            // [0],[1] = active flags (ring of 2), [2] = iterations done
@@ -127,11 +125,6 @@ static int ensure_tables(int device) {
     for (int j = 0; j < kCrcChunks; j++)
       for (uint32_t cc = 0; cc < 32; cc++) tab5[(size_t)((m - 1) * kCrcChunks + j) * 32 + cc] = crc5_entry(m, j, cc);
   CK(cudaMemcpyToSymbol(g_crc5_tab, tab5.data(), sizeof(uint32_t) * (size_t)kCrcTabWords));
-#if ABFT_CRC_MULHI
-  uint32_t mul[8] = {0};
-  for (int j = 1; j < kCrcChunks; j++) mul[j] = 1u << (34 - 5 * j);
-  CK(cudaMemcpyToSymbol(c_crc_mul, mul, sizeof mul));
-#endif
   if (device >= 0 && device < 64) g_tables_ready[device] = true;
   return 0;
 }
@@ -148,8 +141,8 @@ static ReduceOut make_reduce(abft_ctx *c, int slot, abft_comm *comm = nullptr) {
   r.counter = c->d_counter;
   r.dev = c->d_scalars + slot;
   r.host = c->h_scalars + slot;
-  r.host_seq = c->h_seq + slot;
-  r.seq_value = ++c->seq_issued[slot];
+  // (the host polls the mapped word itself: "no value yet" until the reduction's finalizer stores it)
+  memcpy(c->h_scalars + slot, &kSlotEmpty, sizeof(double));
   r.phase = (slot == SLOT_DOT) ? nullptr : c->phase_cur;
   r.phase_slot = (slot == SLOT_SPMV_DOT) ? PH_SPMV_REDUCE : PH_XR_REDUCE;
   r.active = nullptr;
@@ -173,26 +166,24 @@ static int vec_grid(const abft_ctx *c, int N) {
   return (int)std::max(1LL, std::min(want, cap));
 }
 
-// The value of the last reduction into `slot`, as soon as its kernel has published it: the finalizer writes the
-// value and then its sequence number into mapped pinned memory, and the host polls that word instead of paying a
-// stream synchronisation per scalar (two per CG iteration on the plugin path).  Falls back to the stream's status
-// every few thousand polls, so a failed launch surfaces as an error instead of a hang.
+// The value of the last reduction into `slot`, as soon as its kernel has published it: the finalizer stores the
+// value into mapped pinned memory (which make_reduce set to "no value yet"), and the host polls that word instead of
+// paying a stream synchronisation per scalar (two per CG iteration on the plugin path).  Falls back to the stream's
+// status every few thousand polls, so a failed launch surfaces as an error instead of a hang.
 static int wait_scalar(abft_ctx *c, int slot, double *out) {
-  const unsigned int want = c->seq_issued[slot];
-  volatile unsigned int *q = c->h_seq + slot;
-  for (unsigned int spin = 1;; spin++) {
-    if (*q == want) break;
+  volatile unsigned long long *q = reinterpret_cast<volatile unsigned long long *>(c->h_scalars + slot);
+  unsigned long long bits;
+  for (unsigned int spin = 1; (bits = *q) == kSlotEmpty; spin++) {
     if ((spin & 0xFFFu) == 0) {
       const cudaError_t e = cudaStreamQuery(c->stream);
       if (e == cudaSuccess) {
-        if (*q != want) return fail(-1, "reduction finished without publishing its value", __FILE__, __LINE__);
+        if ((bits = *q) == kSlotEmpty) return fail(-1, "reduction finished without publishing its value", __FILE__, __LINE__);
         break;
       }
       if (e != cudaErrorNotReady) return fail((int)e, cudaGetErrorString(e), __FILE__, __LINE__);
     }
   }
-  __atomic_thread_fence(__ATOMIC_ACQUIRE);
-  *out = *(volatile double *)(c->h_scalars + slot);
+  memcpy(out, &bits, sizeof(double));
   return 0;
 }
 
@@ -289,8 +280,6 @@ abft_ctx *abft_cuda_ctx_create(int mode, int device) {
   CKP(cudaMemset(c->d_scalars, 0, sizeof(double) * kNumSlots));
   CKP(cudaHostAlloc(&c->h_scalars, sizeof(double) * kNumSlots, cudaHostAllocMapped));
   memset(c->h_scalars, 0, sizeof(double) * kNumSlots);
-  CKP(cudaHostAlloc(&c->h_seq, sizeof(unsigned int) * kNumSlots, cudaHostAllocMapped));
-  memset(c->h_seq, 0, sizeof(unsigned int) * kNumSlots);
   CKP(cudaMalloc(&c->d_partials, sizeof(double) * kMaxPartials));
   CKP(cudaMalloc(&c->d_counter, sizeof(unsigned int) * 4));
   CKP(cudaMemset(c->d_counter, 0, sizeof(unsigned int) * 4));
@@ -312,7 +301,6 @@ void abft_cuda_ctx_destroy(abft_ctx *c) {
   if (c->h_flag) cudaFreeHost(c->h_flag);
   cudaFree(c->d_scalars);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
-  if (c->h_seq) cudaFreeHost(c->h_seq);
   cudaFree(c->d_partials);
   cudaFree(c->d_counter);
   cudaFree(c->d_loop);
@@ -784,8 +772,7 @@ static int launch_spmv(abft_ctx *c, const abft_matrix *m, const double *x, doubl
   if (m->n_tiles == 0) {
     // no rows: dot(vec, result) over an empty range is 0
     CK(cudaMemsetAsync(red.dev, 0, sizeof(double), c->stream));
-    *const_cast<double *>(red.host) = 0.0;
-    if (red.host_seq) *const_cast<unsigned int *>(red.host_seq) = red.seq_value;
+    if (red.host) *const_cast<double *>(red.host) = 0.0;
     return 0;
   }
   switch (c->mode) {
@@ -1283,6 +1270,7 @@ static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_v
   }
   {
     ReduceOut red = make_reduce(c, SLOT_RR0, m);
+    red.host = nullptr;  // (nobody on the host looks at the scalars while the loop runs: no PCIe store per reduction)
     red.active = flag0;  // iteration 0 reads flag[0]
     red.iters = iters;
     red.threshold = conv_threshold;
@@ -1306,9 +1294,12 @@ static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_v
       // w = A p, pw = p.w (summed over all ranks inside the kernel's finalizer)
       phase_next_row(c);
       WaitSpec wait{m ? m->win[m->rank] : nullptr, m ? m->epoch : 0u, m ? m->wait_mask : 0u, nullptr};
-      if (launch_spmv(c, A, p_full->d, w->d, make_reduce(c, SLOT_SPMV_DOT, m), flag_cur, wait)) return -1;
+      ReduceOut red_pw = make_reduce(c, SLOT_SPMV_DOT, m);
+      red_pw.host = nullptr;
+      if (launch_spmv(c, A, p_full->d, w->d, red_pw, flag_cur, wait)) return -1;
       // alpha = rr / pw ; x += alpha p ; r -= alpha w ; rr_new = r.r
       ReduceOut red = make_reduce(c, slot_new, m);
+      red.host = nullptr;
       red.active = flag_next;
       red.iters = iters;
       red.threshold = conv_threshold;
@@ -1361,7 +1352,9 @@ static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_v
     m->seq = seq0 + 1u + 2u * (unsigned)done_iters;
     m->epoch = epoch0 + 1u + (unsigned)done_iters;
   }
-  if (rr_out) *rr_out = c->h_scalars[(done_iters & 1) ? SLOT_RR1 : SLOT_RR0];
+  if (rr_out && cudaMemcpy(rr_out, c->d_scalars + ((done_iters & 1) ? SLOT_RR1 : SLOT_RR0), sizeof(double),
+                           cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
   return done_iters;
 }
 

@@ -315,9 +315,8 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
     v[k] = s_vals[first + k];
   }
   if (MODE == ABFT_MODE_CONSTRAINTS) c[LEN] = s_cols[first + LEN];
-  // every gather is issued before the first check: the ~35 instructions of one element's check do not cover an L2
-  // round trip, the ~250 of a whole row's do (ncu: 7 % of the stall samples sat on the first DMUL, waiting for the
-  // gather that had been issued last)
+  // every gather is issued before the first check (ncu had 7 % of the stall samples on the first DMUL, waiting for the
+  // gather issued last; ptxas places the loads mid-way through the checks either way: measured neutral, 0.328 ms)
 #pragma unroll
   for (int k = 0; k < LEN; k++) {
     const uint32_t col = ModeTraits<MODE>::masks_column ? (c[k] & 0x00FFFFFFu) : c[k];
@@ -373,12 +372,6 @@ __device__ __forceinline__ bool constraints_fast_ok_row(const uint32_t *cols, ui
 //    A 32-entry table laid out one entry per bank is conflict-free whatever the lanes ask for (same entry = same
 //    address = broadcast).  19 conflict-free lookups per element, 21 tables x 128 B = 2.7 KB per CTA.
 __device__ uint32_t g_crc5_tab[kCrcTabWords];  // [(m-1)*7 + j][c], filled by the host at library init
-#ifndef ABFT_CRC_MULHI
-#define ABFT_CRC_MULHI 0
-#endif
-#if ABFT_CRC_MULHI
-__constant__ uint32_t c_crc_mul[8];            // [j] = 2^(34 - 5j): x * it >> 32 == x >> (5j - 2); filled by the host
-#endif
 __device__ uint32_t g_crc_tab[1024];           // slicing-by-4 byte tables (create_matrix), filled by the host at library init
 
 // CRC-32C of one 32-bit word appended to a running (raw) state; slicing-by-4 tables tab[s*256 + b]
@@ -394,13 +387,10 @@ __device__ __forceinline__ uint32_t crc_map(uint32_t x, const uint32_t *tab) {
 #pragma unroll
   for (int j = 0; j < NCH; j++) {
     // byte offset of entry chunk_j(x) inside its table: the chunk, times 4
-#if ABFT_CRC_MULHI
-    // experiment: the shift as a multiply-high by a power of two the compiler cannot see (IMAD.HI on the FMA pipe, which
-    // this kernel leaves idle, instead of a SHF on the ALU pipe that bounds it)
-    const uint32_t off = (j == 0) ? ((x << 2) & 0x7Cu) : __umulhi(x & (0x1Fu << (5 * j)), c_crc_mul[j]);
-#else
+    // (tried: the shift as a multiply-high by a power of two ptxas cannot see, i.e. IMAD.HI on the idle FMA pipe instead
+    // of SHF on the ALU pipe that bounds this kernel -- ptxas folds the table base into the 64-bit addend and pays for
+    // it with two more moves per lookup: 0.57 ms against 0.47, profiles/r2_ab_session2_block_sizes.jsonl)
     const uint32_t off = (j == 0) ? ((x << 2) & 0x7Cu) : ((x >> (5 * j - 2)) & 0x7Cu);
-#endif
     r ^= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab + ((M - 1) * kCrcChunks + j) * 32) + off);
   }
   return r;
@@ -607,7 +597,7 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
 
 // DYN: the dynamic tile schedule (A.tile_counter), compiled as its own kernel so that the static one carries none of it
 template <int MODE, bool DYN>
-__global__ void __launch_bounds__(SpmvCfg<DYN>::block, (MODE == ABFT_MODE_CRC32C ? 3 : 4) * (kBlock / SpmvCfg<DYN>::block))
+__global__ void __launch_bounds__(SpmvCfg<DYN>::block, 4)
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
             const int *__restrict__ active, WaitSpec wait) {
 #ifndef ABFT_HOST_EMU
@@ -662,6 +652,10 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   if (MODE == ABFT_MODE_CRC32C)
     for (int i = tid; i < kCrcTabWords; i += BLOCK) s_crc[i] = g_crc5_tab[i];
   __syncthreads();
+  // (Tried in round 2 and removed: launching this kernel as a programmatic dependent of calc_p, so that the set-up above
+  // overlaps calc_p's tail.  The stamps of tools/dist_phases.py showed the gap calc_p -> spmv shrink from 6.0 to 2.8 us
+  // at 2 GPUs -- and calc_p and this kernel's own rows grow by 4.7 and 3.7 us, the early CTAs competing with the
+  // predecessor's last ones: 3568 it/s with, 3605 without, profiles/r2_pdl_ab_n1_n2.json.  Round 1 saw the same.)
 
   const uint64_t stream_policy = l2_evict_first_policy();
   // producer (thread 0): stream tile `t` into stage `s`

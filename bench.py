@@ -43,7 +43,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-CHECK_ITERS = 3     # <= the smallest warm-up: the reference arm snapshots it on its way through the warm-up
+CHECK_ITERS = 3     # iterations of the untimed correctness solve both arms print (check.rr, check.x_sum)
 
 
 def parse():
@@ -247,11 +247,12 @@ def cpu_reference_run(args, mode, t, b, iters, warm, check_iters=0):
                 L.orc_calc_p(p, r, rr_new / st["rr"], N)
                 st["rr"] = rr_new
         check = None
-        done = 0
-        if check_iters and check_iters <= warm + iters:
-            k = min(check_iters, warm)
-            run(k); done = k
-        run(warm - done)
+        if check_iters:
+            run(check_iters)
+            check = {"iterations": check_iters, "rr": st["rr"], "x_sum": float(x.sum()), "x_abs_sum": float(np.abs(x).sum())}
+            x[:] = 0.0; r[:] = b; p[:] = b
+            st["rr"] = L.orc_dot(r, r, N)
+        run(warm)
         t0 = time.time()
         run(iters)
         dt = time.time() - t0
@@ -267,16 +268,20 @@ def cpu_reference_run(args, mode, t, b, iters, warm, check_iters=0):
     R.ref_copy_vector(rc.ctx, r, bv)
     R.ref_copy_vector(rc.ctx, p, r)
     rr = ctypes.c_double(R.ref_dot(rc.ctx, r, r))
-    done = 0
     check = None
 
     def run(k):
         return R.ref_cg_iterations(rc.ctx, rc.A, x, r, p, w, k, 0.0, ctypes.byref(rr), None) if k > 0 else 0
-    if check_iters and check_iters <= warm:
-        run(check_iters); done = check_iters
+    if check_iters:
+        # correctness beside the number: a fresh solve of check_iters iterations from x = 0 (our arm does the same)
+        run(check_iters)
         xs = rc.view(x)
         check = {"iterations": check_iters, "rr": rr.value, "x_sum": float(xs.sum()), "x_abs_sum": float(np.abs(xs).sum())}
-    run(warm - done)
+        rc.view(x)[:] = 0.0
+        R.ref_copy_vector(rc.ctx, r, bv)
+        R.ref_copy_vector(rc.ctx, p, r)
+        rr = ctypes.c_double(R.ref_dot(rc.ctx, r, r))
+    run(warm)
     t0 = time.time()
     got = run(iters)
     dt = time.time() - t0
@@ -473,7 +478,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         args.gpus = world
-    warm = max(args.warmup, 3)
+    warm = args.warmup
 
     import pkg_loader
     pkg = pkg_loader.load()

@@ -9,7 +9,7 @@
 #include <string.h>
 
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorNotSupported = 801, cudaErrorPeerAccessAlreadyEnabled = 704 };
+enum { cudaSuccess = 0, cudaErrorNotReady = 600, cudaErrorNotSupported = 801, cudaErrorPeerAccessAlreadyEnabled = 704 };
 typedef struct emu_stream_t *cudaStream_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaHostAllocMapped = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
@@ -26,6 +26,7 @@ static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : 2; }
 template <class T> static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }

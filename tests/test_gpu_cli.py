@@ -137,7 +137,7 @@ def _ngpus():
 @pytest.mark.parametrize("mode", ["none", "secded", "constraints", "crc32c"])
 def test_multi_gpu_cli_matches_cpu_target(O, exe, mtx256, mode):
     """ABFT_CUDA_NGPUS=g: the plugin row-partitions the matrix over g GPUs of the box; same output as -t cpu."""
-    g = min(_ngpus(), 4)
+    g = min(_ngpus(), 8)
     if g < 2:
         pytest.skip("needs >= 2 GPUs")
     args = ["-f", mtx256, "-b", "1", "-c", "1e-10", "-m"]
@@ -152,7 +152,7 @@ def test_multi_gpu_cli_matches_cpu_target(O, exe, mtx256, mode):
 def test_multi_gpu_cli_fixture_replay(O, exe, mtx32, golden_cli):
     """The pinned-seed injection fixtures with the matrix split over the GPUs: same flips (routed to the owning
     GPU), same messages with global indices, same exit status."""
-    g = min(_ngpus(), 4)
+    g = min(_ngpus(), 8)
     if g < 2:
         pytest.skip("needs >= 2 GPUs")
     for case in golden_cli["cases"]:
