@@ -13,11 +13,14 @@ for n in ${SCALE:-$N}; do
     timeout 400 python bench.py --gpus 1 --steps ${STEPS:-100} --warmup 5 --all-modes 0 --no-cpu-baseline ${BENCH_EXTRA:-} > gpurun_out/r2_dist_bench_n$n.json 2> gpurun_out/r2_dist_bench_n$n.err
   else
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) \
-        bench.py --gpus $n --steps ${STEPS:-100} --warmup 5 ${BENCH_EXTRA:-} > gpurun_out/r2_dist_bench_n$n.json 2> gpurun_out/r2_dist_bench_n$n.err
+        bench.py --gpus $n --steps ${STEPS:-100} --warmup 5 $( [ "$n" -eq "$N" ] && echo "${BENCH_EXTRA_TOP:-}" || echo "${BENCH_EXTRA:-}" ) > gpurun_out/r2_dist_bench_n$n.json 2> gpurun_out/r2_dist_bench_n$n.err
   fi
   el "bench N=$n rc=$?"; tail -1 gpurun_out/r2_dist_bench_n$n.json | cut -c1-900; tail -2 gpurun_out/r2_dist_bench_n$n.err | cut -c1-300
 done
 if [ "$N" -ge 2 ]; then
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29650 \
+      bench.py --impl reference --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_dist_bench_ref_torchrun.json 2> gpurun_out/r2_dist_bench_ref_torchrun.err
+  el "reference arm under torchrun rc=$?"; cut -c1-700 gpurun_out/r2_dist_bench_ref_torchrun.json
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29700 \
       tools/dist_phases.py --iters 60 --out gpurun_out/r2_dist_phases_n$N.json > gpurun_out/r2_dist_phases_n$N.log 2>&1
   el "phase stamps N=$N rc=$?"; tail -12 gpurun_out/r2_dist_phases_n$N.log | cut -c1-200
