@@ -12,8 +12,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ABFT_CUDA_LIB") or os.path.join(HERE, "libabftcuda.so")   # override: kernel experiments
 
-MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"]
-FATAL_KINDS = {1, 4, 5, 6, 7, 8, 9, 11, 12}
+MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c", "secdedv"]
+FATAL_KINDS = {1, 4, 5, 6, 7, 8, 9, 11, 12, 13}
 
 # every extern "C" symbol include/abft_cuda.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -25,7 +25,7 @@ SYMBOLS = [
     "abft_cuda_plan_tiles", "abft_cuda_plan_matrix", "abft_cuda_matrix_rows", "abft_cuda_matrix_nnz", "abft_cuda_matrix_read", "abft_cuda_matrix_poke_rowptr",
     "abft_cuda_matrix_poke_col", "abft_cuda_matrix_poke_value",
     "abft_cuda_vector_create", "abft_cuda_vector_wrap", "abft_cuda_vector_view", "abft_cuda_vector_destroy",
-    "abft_cuda_vector_len", "abft_cuda_vector_dev_ptr", "abft_cuda_vector_map", "abft_cuda_vector_unmap",
+    "abft_cuda_vector_len", "abft_cuda_vector_flip_bit", "abft_cuda_vector_dev_ptr", "abft_cuda_vector_map", "abft_cuda_vector_unmap",
     "abft_cuda_vector_copy",
     "abft_cuda_spmv", "abft_cuda_dot", "abft_cuda_calc_xr", "abft_cuda_calc_p",
     "abft_cuda_dot_async", "abft_cuda_calc_xr_async", "abft_cuda_scalar_dev_ptr", "abft_cuda_scalar_host",
@@ -101,6 +101,7 @@ def load():
     sig("abft_cuda_vector_view", vp, vp, vp, i32, i32)
     sig("abft_cuda_vector_destroy", None, vp, vp)
     sig("abft_cuda_vector_len", i32, vp)
+    sig("abft_cuda_vector_flip_bit", i32, vp, vp, i32, i32)
     sig("abft_cuda_vector_dev_ptr", vp, vp)
     sig("abft_cuda_vector_map", f64p, vp, vp)
     sig("abft_cuda_vector_unmap", i32, vp, vp, vp)

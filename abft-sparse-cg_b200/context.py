@@ -138,6 +138,10 @@ class CUDAContext:
     def download(self, v) -> np.ndarray:
         return self.map_vector(v).copy()
 
+    def flip_vector_bit(self, v, index, bit):
+        """mode secdedv's injection aid: flip one bit of a vector element on the device"""
+        self._ck(self.L.abft_cuda_vector_flip_bit(self.ctx, v.handle, int(index), int(bit)), "vector_flip_bit")
+
     # ---- hot path ----
     def dot(self, a, b) -> float:
         out = C.c_double(0.0)

@@ -69,7 +69,9 @@ struct abft_matrix {
 };
 
 struct abft_ctx {
-  int mode = 0;
+  int mode = 0;      // public mode (include/abft_cuda.h)
+  int base = 0;      // the matrix code it implies (secdedv: secded)
+  bool vsed = false; // mode secdedv: parity bit in every vector element, row pointers protected
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -110,7 +112,7 @@ struct abft_comm {
   unsigned int epoch = 0;  // pushes issued so far
 };
 
-static const char *kModeNames[ABFT_MODE_COUNT] = {"none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"};
+static const char *kModeNames[ABFT_MODE_COUNT] = {"none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c", "secdedv"};
 
 static bool g_tables_ready[64] = {false};
 
@@ -232,6 +234,10 @@ int abft_cuda_format_event(const abft_event *e, char *buf, int buflen) {
     case ABFT_EV_CRC_ROW: return snprintf(buf, buflen, "[CRC32C] error detected in row %d", (int)e->index);
     case ABFT_EV_ROWPTR_CORRECTED: return snprintf(buf, buflen, "[ROWS] corrected bit %u of row pointer pair %d", e->bit, (int)e->index);
     case ABFT_EV_ROWPTR_DOUBLE: return snprintf(buf, buflen, "[ROWS] double-bit error detected in row pointer pair %d", (int)e->index);
+    case ABFT_EV_VECTOR_SED: {
+      static const char *const names[] = {"?", "spmv operand", "x", "r", "p", "w", "dot a", "dot b", "mapped"};
+      return snprintf(buf, buflen, "[ECC] error detected in vector (%s) at index %d", names[e->bit < 9 ? e->bit : 0], (int)e->index);
+    }
     case ABFT_EV_LOG_OVERFLOW:
       return e->bit ? snprintf(buf, buflen, "stray list overflow: %d rerouted products dropped", (int)e->index)
                     : snprintf(buf, buflen, "fault log overflow: %d events dropped", (int)e->index);
@@ -267,6 +273,8 @@ abft_ctx *abft_cuda_ctx_create(int mode, int device) {
     }
   } cleanup{c};
   c->mode = mode;
+  c->vsed = mode == ABFT_MODE_SECDEDV;
+  c->base = c->vsed ? ABFT_MODE_SECDED : mode;
   c->device = device;
   cudaDeviceProp prop;
   CKP(cudaGetDeviceProperties(&prop, device));
@@ -445,7 +453,7 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
     fail(-1, "bad arguments to matrix_create", __FILE__, __LINE__);
     return nullptr;
   }
-  if (c->mode >= ABFT_MODE_SED && (unsigned)N_global > (1u << 24)) {
+  if (c->base >= ABFT_MODE_SED && (unsigned)N_global > (1u << 24)) {
     fail(-1, "ECC modes keep the check bits in column bits 24..31: N must be <= 2^24", __FILE__, __LINE__);
     return nullptr;
   }
@@ -486,20 +494,21 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
   rowptr_kernel<<<grid, kBlock, 0, c->stream>>>(d_coo_rows, (uint32_t)nnz, (uint32_t)n_rows, (uint32_t)row_offset,
                                                 m->d_rowptr);
   c->launches++;
-  if (c->mode >= ABFT_MODE_SED && c->mode <= ABFT_MODE_SECDED && nnz > 0) {
-    encode_elements_kernel<<<grid, kBlock, 0, c->stream>>>(c->mode, m->view.cols, m->view.values, (uint32_t)nnz);
+  if (c->base >= ABFT_MODE_SED && c->base <= ABFT_MODE_SECDED && nnz > 0) {
+    encode_elements_kernel<<<grid, kBlock, 0, c->stream>>>(c->base, m->view.cols, m->view.values, (uint32_t)nnz);
     c->launches++;
-  } else if (c->mode == ABFT_MODE_CRC32C && n_rows > 0) {
+  } else if (c->base == ABFT_MODE_CRC32C && n_rows > 0) {
     encode_crc_rows_kernel<<<grid, kBlock, 0, c->stream>>>(m->d_rowptr, m->view.cols, m->view.values, (uint32_t)n_rows);
     c->launches++;
   }
   CKP(cudaGetLastError());
   bool protect_rows = false;
   {
-    const char *pr = getenv("ABFT_CUDA_PROTECT_ROWS");
+    // mode secdedv protects the row pointers; ABFT_CUDA_PROTECT_ROWS=secded asks for it in any other mode
+    const char *pr = c->vsed ? "secded" : getenv("ABFT_CUDA_PROTECT_ROWS");
     if (pr && *pr && strcmp(pr, "0") && strcmp(pr, "none")) {
       if (strcmp(pr, "secded") || nnz >= (1 << 28) || (row_offset & 1)) {
-        fail(-1, "ABFT_CUDA_PROTECT_ROWS: only `secded` exists; it needs nnz < 2^28 and partitions that start on even rows",
+        fail(-1, "row-pointer protection (mode secdedv, ABFT_CUDA_PROTECT_ROWS): only `secded` exists; it needs nnz < 2^28 and partitions that start on even rows",
              __FILE__, __LINE__);
         return nullptr;
       }
@@ -522,7 +531,7 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
   CKP(cudaFree(d_coo_rows));
   d_coo_rows = nullptr;
   std::vector<Tile> tiles;
-  const int kind = plan_matrix(h_rowptr.data(), (uint32_t)n_rows, c->mode, tiles);
+  const int kind = plan_matrix(h_rowptr.data(), (uint32_t)n_rows, c->base, tiles);
   m->n_tiles = (int)tiles.size();
   if (m->n_tiles > kMaxPartials) {   // (one reduction partial per tile or CTA)
     fail(-1, "matrix needs more spmv tiles than the reduction buffer holds", __FILE__, __LINE__);
@@ -689,6 +698,19 @@ void abft_cuda_vector_destroy(abft_ctx *c, abft_vector *v) {
   delete v;
 }
 
+// fault injection into a vector (the reference injects into the matrix only, CSR/CPUContext.cpp:135-159): flips one bit
+// of element `index` on the device, through the same tiny kernel as the matrix poke
+int abft_cuda_vector_flip_bit(abft_ctx *c, abft_vector *v, int index, int bit) {
+  REQUIRE(c && v, "null argument");
+  REQUIRE(index >= 0 && index < v->N && bit >= 0 && bit < 64, "vector_flip_bit: index or bit out of range");
+  CK(cudaSetDevice(c->device));
+  flip_word_bit_kernel<<<1, 1, 0, c->stream>>>(reinterpret_cast<uint32_t *>(v->d + index) + bit / 32, bit % 32);
+  c->launches++;
+  c->epoch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int abft_cuda_vector_len(const abft_vector *v) { return v ? v->N : -1; }
 double *abft_cuda_vector_dev_ptr(abft_vector *v) { return v ? v->d : nullptr; }
 
@@ -699,6 +721,11 @@ double *abft_cuda_vector_map(abft_ctx *c, abft_vector *v) {
   }
   CKP(cudaSetDevice(c->device));
   if (!v->h_stage) CKP(cudaHostAlloc(&v->h_stage, sizeof(double) * (size_t)std::max(v->N, 1), cudaHostAllocDefault));
+  if (c->vsed && v->N) {
+    // mode secdedv: the vector is checked on its way out (the host gets the stored values, parity bit and all)
+    vec_check_kernel<<<vec_grid(c, v->N), kBlock, 0, c->stream>>>(v->d, v->N, LogRef{c->d_log, c->h_flag});
+    c->launches++;
+  }
   if (v->N) CKP(cudaMemcpyAsync(v->h_stage, v->d, sizeof(double) * (size_t)v->N, cudaMemcpyDeviceToHost, c->stream));
   CKP(cudaStreamSynchronize(c->stream));
   return v->h_stage;
@@ -708,6 +735,11 @@ int abft_cuda_vector_unmap(abft_ctx *c, abft_vector *v, const double *h) {
   REQUIRE(c && v && (h || v->N == 0), "null argument");
   CK(cudaSetDevice(c->device));
   if (v->N) CK(cudaMemcpyAsync(v->d, h, sizeof(double) * (size_t)v->N, cudaMemcpyHostToDevice, c->stream));
+  if (c->vsed && v->N) {
+    // mode secdedv: every element gets its parity bit (in place of the mantissa's lowest bit) as it arrives
+    vec_encode_kernel<<<vec_grid(c, v->N), kBlock, 0, c->stream>>>(v->d, v->N);
+    c->launches++;
+  }
   // pageable sources are staged by the driver before the call returns; a pinned
   // source (our own staging buffer) must not be reused before the copy ran
   if (h != v->h_stage) CK(cudaStreamSynchronize(c->stream));
@@ -783,6 +815,7 @@ static int launch_spmv(abft_ctx *c, const abft_matrix *m, const double *x, doubl
     case ABFT_MODE_SEC8: launch_spmv_mode<ABFT_MODE_SEC8>(c, m, x, y, red, active, wait); break;
     case ABFT_MODE_SECDED: launch_spmv_mode<ABFT_MODE_SECDED>(c, m, x, y, red, active, wait); break;
     case ABFT_MODE_CRC32C: launch_spmv_mode<ABFT_MODE_CRC32C>(c, m, x, y, red, active, wait); break;
+    case ABFT_MODE_SECDEDV: launch_spmv_mode<ABFT_MODE_SECDED | kVecSed>(c, m, x, y, red, active, wait); break;
     default: return fail(-1, "bad mode", __FILE__, __LINE__);
   }
   c->launches++;
@@ -812,7 +845,9 @@ int abft_cuda_spmv(abft_ctx *c, abft_matrix *m, const abft_vector *vec, abft_vec
 
 static int launch_dot(abft_ctx *c, const double *a, const double *b, int N, const ReduceOut &red, const int *active) {
   const int ok = aligned16(a) && aligned16(b);
-  dot_kernel<<<vec_grid(c, N), kBlock, 0, c->stream>>>(a, b, N, ok, red, active);
+  const LogRef L{c->d_log, c->h_flag};
+  if (c->vsed) { dot_kernel<true><<<vec_grid(c, N), kBlock, 0, c->stream>>>(a, b, N, ok, red, active, L); }
+  else { dot_kernel<false><<<vec_grid(c, N), kBlock, 0, c->stream>>>(a, b, N, ok, red, active, L); }
   c->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -844,10 +879,11 @@ int abft_cuda_dot(abft_ctx *c, const abft_vector *a, const abft_vector *b, doubl
 static int launch_calc_xr(abft_ctx *c, double *x, double *r, const double *p, const double *w, const ScalarArg &alpha,
                           bool dev, int N, const ReduceOut &red, const int *active) {
   const int ok = aligned16(x) && aligned16(r) && aligned16(p) && aligned16(w);
-  if (dev)
-    calc_xr_kernel<true><<<vec_grid(c, N), kBlock, 0, c->stream>>>(x, r, p, w, alpha, N, ok, red, active);
-  else
-    calc_xr_kernel<false><<<vec_grid(c, N), kBlock, 0, c->stream>>>(x, r, p, w, alpha, N, ok, red, active);
+  const LogRef L{c->d_log, c->h_flag};
+  if (dev && c->vsed) { calc_xr_kernel<true, true><<<vec_grid(c, N), kBlock, 0, c->stream>>>(x, r, p, w, alpha, N, ok, red, active, L); }
+  else if (dev) { calc_xr_kernel<true, false><<<vec_grid(c, N), kBlock, 0, c->stream>>>(x, r, p, w, alpha, N, ok, red, active, L); }
+  else if (c->vsed) { calc_xr_kernel<false, true><<<vec_grid(c, N), kBlock, 0, c->stream>>>(x, r, p, w, alpha, N, ok, red, active, L); }
+  else { calc_xr_kernel<false, false><<<vec_grid(c, N), kBlock, 0, c->stream>>>(x, r, p, w, alpha, N, ok, red, active, L); }
   c->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -876,10 +912,11 @@ int abft_cuda_calc_xr(abft_ctx *c, abft_vector *x, abft_vector *r, const abft_ve
 static int launch_calc_p(abft_ctx *c, double *p, const double *r, const ScalarArg &beta, bool dev, int N,
                          const int *active) {
   const int ok = aligned16(p) && aligned16(r);
-  if (dev)
-    calc_p_kernel<true><<<vec_grid(c, N), kBlock, 0, c->stream>>>(p, r, beta, N, ok, active);
-  else
-    calc_p_kernel<false><<<vec_grid(c, N), kBlock, 0, c->stream>>>(p, r, beta, N, ok, active);
+  const LogRef L{c->d_log, c->h_flag};
+  if (dev && c->vsed) { calc_p_kernel<true, true><<<vec_grid(c, N), kBlock, 0, c->stream>>>(p, r, beta, N, ok, active, L); }
+  else if (dev) { calc_p_kernel<true, false><<<vec_grid(c, N), kBlock, 0, c->stream>>>(p, r, beta, N, ok, active, L); }
+  else if (c->vsed) { calc_p_kernel<false, true><<<vec_grid(c, N), kBlock, 0, c->stream>>>(p, r, beta, N, ok, active, L); }
+  else { calc_p_kernel<false, false><<<vec_grid(c, N), kBlock, 0, c->stream>>>(p, r, beta, N, ok, active, L); }
   c->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -933,7 +970,7 @@ int abft_cuda_poll_events(abft_ctx *c, abft_event *out, int cap, int *fatal) {
 
     // serial order of the reference: rows ascending; within a row the row checks
     // come before its elements, elements ascending (CSR/CPUContext.cpp:166-206)
-    const bool cons = c->mode == ABFT_MODE_CONSTRAINTS;
+    const bool cons = c->base == ABFT_MODE_CONSTRAINTS;
     auto key = [&](const abft_event &e, uint64_t &k1, int &k2, uint64_t &k3) {
       const bool rowev = e.kind == ABFT_EV_ROW_SIZE || e.kind == ABFT_EV_ROW_ORDER || e.kind == ABFT_EV_CRC_ROW;
       if (cons) {
@@ -1133,8 +1170,9 @@ static int launch_push(abft_ctx *c, abft_comm *m, abft_vector *p_local, const ab
   const int N = p_local->N;
   long long want = ((long long)N + kBlock * 8 - 1) / (kBlock * 8);
   const int grid = (int)std::max(1LL, std::min(want, (long long)c->num_sms * 8));
-  calc_p_push_kernel<false, COMPUTE><<<grid, kBlock, 0, c->stream>>>(p_local->d, COMPUTE ? r->d : p_local->d, b, N, plan,
-                                                                     nullptr);
+  const LogRef L{c->d_log, c->h_flag};
+  if (c->vsed) { calc_p_push_kernel<false, COMPUTE, true><<<grid, kBlock, 0, c->stream>>>(p_local->d, COMPUTE ? r->d : p_local->d, b, N, plan, nullptr, L); }
+  else { calc_p_push_kernel<false, COMPUTE, false><<<grid, kBlock, 0, c->stream>>>(p_local->d, COMPUTE ? r->d : p_local->d, b, N, plan, nullptr, L); }
   c->launches++;
   c->epoch++;
   CK(cudaGetLastError());
@@ -1265,7 +1303,7 @@ static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_v
     PushPlan plan{};
     push_plan(plan);
     ScalarArg none{0.0, nullptr, nullptr};
-    calc_p_push_kernel<false, false><<<push_grid, kBlock, 0, s>>>(p_local->d, p_local->d, none, N, plan, nullptr);
+    calc_p_push_kernel<false, false, false><<<push_grid, kBlock, 0, s>>>(p_local->d, p_local->d, none, N, plan, nullptr, LogRef{c->d_log, c->h_flag});
     c->launches++;
   }
   {
@@ -1312,7 +1350,8 @@ static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_v
       if (m) {
         PushPlan plan{};
         push_plan(plan);
-        calc_p_push_kernel<true, true><<<push_grid, kBlock, 0, s>>>(p_local->d, r->d, beta, N, plan, flag_cur);
+        if (c->vsed) { calc_p_push_kernel<true, true, true><<<push_grid, kBlock, 0, s>>>(p_local->d, r->d, beta, N, plan, flag_cur, LogRef{c->d_log, c->h_flag}); }
+        else { calc_p_push_kernel<true, true, false><<<push_grid, kBlock, 0, s>>>(p_local->d, r->d, beta, N, plan, flag_cur, LogRef{c->d_log, c->h_flag}); }
         c->launches++;
       } else if (launch_calc_p(c, p_local->d, r->d, beta, true, N, flag_cur)) {
         return -1;
@@ -1499,8 +1538,8 @@ abft_coo_matrix *abft_cuda_coo_matrix_create(abft_ctx *c, const uint32_t *column
     fail(-1, "bad arguments to coo_matrix_create", __FILE__, __LINE__);
     return nullptr;
   }
-  if (c->mode == ABFT_MODE_CRC32C) {
-    fail(-1, "crc32c is a CSR-only mode (the reference's COO target has none, and this repository defines none)",
+  if (c->mode == ABFT_MODE_CRC32C || c->mode == ABFT_MODE_SECDEDV) {
+    fail(-1, "crc32c / secdedv are CSR-only modes (the reference's COO target has none, and this repository defines none)",
          __FILE__, __LINE__);
     return nullptr;
   }

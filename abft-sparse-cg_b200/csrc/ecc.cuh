@@ -102,6 +102,23 @@ __device__ __forceinline__ uint32_t encode_column(int mode, uint32_t w0, uint32_
 }
 
 // ---------------------------------------------------------------------------
+// Vector protection (mode secdedv; repository-defined): SED over every double of x, r, p, w -- the
+// mantissa's least significant bit is given up for the parity of the other 63 bits, so a stored element always has
+// even parity and a single flipped bit anywhere in it is detected when the element is next read.  The reference
+// protects no vector (CSR/CPUContext.cpp:54-113); this costs one ulp of precision per stored value.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double vec_encode(double v) {
+  const uint32_t lo = (uint32_t)__double2loint(v) & ~1u, hi = (uint32_t)__double2hiint(v);
+  return __hiloint2double((int)hi, (int)(lo | ((uint32_t)__popc(lo ^ hi) & 1u)));
+}
+// bit 0 set iff the element's parity is odd (corrupted); callers OR the raw popcounts and test bit 0 once
+__device__ __forceinline__ uint32_t vec_parity_bits(double v) {
+  return (uint32_t)__popc((uint32_t)__double2loint(v) ^ (uint32_t)__double2hiint(v));
+}
+// which vector a detected fault was found in (the `bit` field of ABFT_EV_VECTOR_SED)
+enum { VEC_SPMV_OPERAND = 1, VEC_X = 2, VEC_R = 3, VEC_P = 4, VEC_W = 5, VEC_DOT_A = 6, VEC_DOT_B = 7, VEC_MAPPED = 8 };
+
+// ---------------------------------------------------------------------------
 // CRC-32C (Castagnoli, reflected 0x82F63B78), repo-defined row code
 // ---------------------------------------------------------------------------
 constexpr uint32_t crc32c_table_entry(uint32_t i, int slice) {

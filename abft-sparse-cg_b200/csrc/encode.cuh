@@ -94,5 +94,6 @@ __global__ void flip_bit_kernel(uint32_t *cols, double *values, uint32_t index, 
 }
 
 __global__ void poke_u32_kernel(uint32_t *p, uint32_t value) { *p = value; }
+__global__ void flip_word_bit_kernel(uint32_t *p, int bit) { *p ^= 1u << bit; }
 
 }  // namespace abft

@@ -183,12 +183,12 @@ __device__ __noinline__ uint4 handle_fault(uint32_t w0, uint32_t w1, uint32_t co
                                            volatile unsigned int *flag) {
   const LogRef L{log, flag};
   uint32_t changed = 0;
-  if (MODE == ABFT_MODE_SED) {
+  if ((MODE & 7) == ABFT_MODE_SED) {
     log_event(L, ABFT_EV_SED_DETECTED, gindex, 0);
   } else {
     const uint32_t odd = overall_parity(w0, w1, col);
     const uint32_t s = syndrome7(w0, w1, col);
-    const bool correct = (MODE == ABFT_MODE_SEC7) ? (s != 0) : (odd != 0);
+    const bool correct = ((MODE & 7) == ABFT_MODE_SEC7) ? (s != 0) : (odd != 0);
     if (correct) {
       if (s) {
         const uint32_t bit = flipped_bit(s);
@@ -201,7 +201,7 @@ __device__ __noinline__ uint4 handle_fault(uint32_t w0, uint32_t w1, uint32_t co
         log_event(L, ABFT_EV_CORRECTED_PARITY, gindex, 0);
       }
       changed = 1;
-    } else if (MODE == ABFT_MODE_SECDED && s) {
+    } else if ((MODE & 7) == ABFT_MODE_SECDED && s) {
       log_event(L, ABFT_EV_DOUBLE_BIT, gindex, 0);
     }
   }
@@ -211,9 +211,9 @@ __device__ __noinline__ uint4 handle_fault(uint32_t w0, uint32_t w1, uint32_t co
 // bit 0 set iff the element fails the mode's fast check
 template <int MODE>
 __device__ __forceinline__ uint32_t element_suspect(uint32_t w0, uint32_t w1, uint32_t col) {
-  if (MODE == ABFT_MODE_SED || MODE == ABFT_MODE_SEC8) return overall_parity(w0, w1, col);
-  if (MODE == ABFT_MODE_SEC7) return syndrome7_any(w0, w1, col);
-  if (MODE == ABFT_MODE_SECDED) return (overall_parity(w0, w1, col) | syndrome7_any(w0, w1, col)) & 1u;
+  if ((MODE & 7) == ABFT_MODE_SED || (MODE & 7) == ABFT_MODE_SEC8) return overall_parity(w0, w1, col);
+  if ((MODE & 7) == ABFT_MODE_SEC7) return syndrome7_any(w0, w1, col);
+  if ((MODE & 7) == ABFT_MODE_SECDED) return (overall_parity(w0, w1, col) | syndrome7_any(w0, w1, col)) & 1u;
   return 0;
 }
 
@@ -221,21 +221,25 @@ __device__ __forceinline__ uint32_t element_suspect(uint32_t w0, uint32_t w1, ui
 // bit 0 once.  Written as a flat chain of 3-input ORs (one LOP3 each).
 template <int MODE>
 __device__ __forceinline__ uint32_t or_suspect_bits(uint32_t acc, uint32_t w0, uint32_t w1, uint32_t col) {
-  if (MODE == ABFT_MODE_SED || MODE == ABFT_MODE_SEC8) return acc | __popc(w0 ^ w1 ^ col);
-  if (MODE == ABFT_MODE_SEC7 || MODE == ABFT_MODE_SECDED) {
+  if ((MODE & 7) == ABFT_MODE_SED || (MODE & 7) == ABFT_MODE_SEC8) return acc | __popc(w0 ^ w1 ^ col);
+  if ((MODE & 7) == ABFT_MODE_SEC7 || (MODE & 7) == ABFT_MODE_SECDED) {
     acc = acc | __popc(masked<1>(w0, w1, col)) | __popc(masked<2>(w0, w1, col));
     acc = acc | __popc(masked<3>(w0, w1, col)) | __popc(masked<4>(w0, w1, col));
     acc = acc | __popc(masked<5>(w0, w1, col)) | __popc(masked<6>(w0, w1, col));
-    if (MODE == ABFT_MODE_SECDED) acc = acc | __popc(masked<7>(w0, w1, col)) | __popc(w0 ^ w1 ^ col);
+    if ((MODE & 7) == ABFT_MODE_SECDED) acc = acc | __popc(masked<7>(w0, w1, col)) | __popc(w0 ^ w1 ^ col);
     else acc = acc | __popc(masked<7>(w0, w1, col));
   }
   return acc;
 }
 
+// MODE, throughout this file: the ABFT mode in bits 0..2; bit 3 (kVecSed) adds the vector protection of mode secdedv
+// (ecc.cuh: parity in every vector element's lowest mantissa bit) to what the kernel does for the base mode.
+constexpr int kVecSed = 8;
 template <int MODE>
 struct ModeTraits {
-  static constexpr bool per_element_ecc = MODE >= ABFT_MODE_SED && MODE <= ABFT_MODE_SECDED;
-  static constexpr bool masks_column = MODE >= ABFT_MODE_SED;  // check bits in column bits 24..31
+  static constexpr bool per_element_ecc = (MODE & 7) >= ABFT_MODE_SED && (MODE & 7) <= ABFT_MODE_SECDED;
+  static constexpr bool masks_column = (MODE & 7) >= ABFT_MODE_SED;  // check bits in column bits 24..31
+  static constexpr bool vec_sed = (MODE & kVecSed) != 0;
 };
 
 // check (and repair) one element, gather vec[col], return the rounded product
@@ -258,6 +262,7 @@ __device__ __forceinline__ double element_product(uint32_t cw, double v, uint32_
   const uint32_t col = ModeTraits<MODE>::masks_column ? (cw & 0x00FFFFFFu) : cw;
   // a column no check caught can point outside vec[] (the reference reads out of bounds: UB): clamp it
   const double xv = __ldg(x + min(col, A.n_cols - 1u));
+  if (ModeTraits<MODE>::vec_sed && (vec_parity_bits(xv) & 1u)) log_event(L, ABFT_EV_VECTOR_SED, min(col, A.n_cols - 1u), VEC_SPMV_OPERAND);
   return __dmul_rn(v, xv);
 }
 
@@ -280,6 +285,7 @@ __device__ __forceinline__ void batch_products(const uint32_t (&li)[U], const ui
     }
     uint32_t col = ModeTraits<MODE>::masks_column ? (cw[k] & 0x00FFFFFFu) : cw[k];
     xv[k] = __ldg(x + min(col, A.n_cols - 1u));
+    if (ModeTraits<MODE>::vec_sed) suspect |= vec_parity_bits(xv[k]);
   }
   if (!(suspect & 1u)) {
 #pragma unroll
@@ -314,7 +320,7 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
     c[k] = s_cols[first + k];
     v[k] = s_vals[first + k];
   }
-  if (MODE == ABFT_MODE_CONSTRAINTS) c[LEN] = s_cols[first + LEN];
+  if ((MODE & 7) == ABFT_MODE_CONSTRAINTS) c[LEN] = s_cols[first + LEN];
   // every gather is issued before the first check (ncu had 7 % of the stall samples on the first DMUL, waiting for the
   // gather issued last; ptxas places the loads mid-way through the checks either way: measured neutral, 0.328 ms)
 #pragma unroll
@@ -328,7 +334,7 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
   }
 #pragma unroll
   for (int k = 0; k < LEN; k++) {
-    if (MODE == ABFT_MODE_CONSTRAINTS) {
+    if ((MODE & 7) == ABFT_MODE_CONSTRAINTS) {
       // CSR/CPUContext.cpp:188-200: col < N, and strictly increasing inside the row
       suspect |= (c[k] >= n_cols) ? 1u : 0u;
       suspect |= ((uint32_t)(k + 1) < count && c[k + 1] <= c[k]) ? 1u : 0u;
@@ -338,6 +344,7 @@ __device__ __forceinline__ double walk_chunk(double sum, uint32_t first, uint32_
       split_value(v[k], w0, w1);
       suspect = or_suspect_bits<MODE>(suspect, w0, w1, c[k]);
     }
+    if (ModeTraits<MODE>::vec_sed) suspect |= vec_parity_bits(xv[k]);  // (the one-by-one path names the element)
   }
   if (full) {
 #pragma unroll
@@ -518,7 +525,7 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
     rs = s_rptr[row - rb];
     re = s_rptr[row + 1 - rb];
     xrow = __ldg(x + A.row_offset + row);   // dot()'s operand: in flight behind the walk, not after it
-    if (MODE != ABFT_MODE_CONSTRAINTS) {
+    if ((MODE & 7) != ABFT_MODE_CONSTRAINTS) {
       // these modes trust rows[] like the reference; clamp so a bad pointer cannot fault
       rs = min(max(rs, t.nnz_begin), t.nnz_end);
       re = min(max(re, rs), t.nnz_end);
@@ -527,7 +534,7 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
   const uint32_t len = re - rs;
   // (CONSTRAINTS: only if its row pointers keep the row inside the staged window; anything else,
   // i.e. a corrupted rows[], takes the careful path that mirrors the reference's checks one by one)
-  const bool in_window = MODE != ABFT_MODE_CONSTRAINTS || (rs >= t.nnz_begin && re <= t.nnz_end && rs <= re);
+  const bool in_window = (MODE & 7) != ABFT_MODE_CONSTRAINTS || (rs >= t.nnz_begin && re <= t.nnz_end && rs <= re);
   // does every row of this warp fill the unrolled walk?  Lanes without a row do not veto.
   const bool full_rows = max_len <= 7 && __all_sync(0xffffffffu, !has_row || (in_window && len == need));
   if (!has_row) return;
@@ -535,7 +542,7 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
   bool careful = true;
   const uint32_t *sc = s_cols + (rs - cb);
   const double *sv = s_vals + (rs - vb);
-  if (MODE != ABFT_MODE_CRC32C && in_window) {
+  if ((MODE & 7) != ABFT_MODE_CRC32C && in_window) {
     uint32_t suspect = 0;
     // max_len is what create_matrix saw.  A corrupted rows[] can make this row longer while keeping it inside
     // the window; the reference walks the whole [start, end) range (CSR/CPUContext.cpp:125,184), so such a
@@ -552,7 +559,7 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
         sum = walk_chunk<MODE, 4>(sum, base, len - base, sc, sv, A.n_cols, x, suspect);
     careful = (suspect & 1u) != 0;  // a check tripped somewhere in this row: walk it again, carefully
   }
-  if (MODE == ABFT_MODE_CRC32C && max_len <= 7 && len >= 4 && len <= need) {
+  if ((MODE & 7) == ABFT_MODE_CRC32C && max_len <= 7 && len >= 4 && len <= need) {
     bool bad = false;
     if (max_len <= 4) sum = walk_crc<4>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
     else if (max_len == 5) sum = walk_crc<5>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
@@ -563,9 +570,9 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
   }
   if (careful) {
     sum = 0.0;
-    if (MODE == ABFT_MODE_CONSTRAINTS) {
+    if ((MODE & 7) == ABFT_MODE_CONSTRAINTS) {
       sum = constraints_careful_row(row, rs, re, t, s_cols, s_vals, cb, vb, true, A, x, L);
-    } else if (MODE == ABFT_MODE_CRC32C) {
+    } else if ((MODE & 7) == ABFT_MODE_CRC32C) {
       uint32_t crc = 0xFFFFFFFFu, stored = 0;
       bool bad = false;
       for (uint32_t i = rs; i < re; i++) {
@@ -591,6 +598,10 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
         sum = __dadd_rn(sum, element_product<MODE>(s_cols[i - cb], s_vals[i - vb], i, A, x, L));
     }
   }
+  if (ModeTraits<MODE>::vec_sed) {
+    if (vec_parity_bits(xrow) & 1u) log_event(L, ABFT_EV_VECTOR_SED, A.row_offset + row, VEC_SPMV_OPERAND);
+    sum = vec_encode(sum);   // what is stored is what dot() and calc_xr will read
+  }
   y[row] = sum;
   dot_part = __dadd_rn(dot_part, __dmul_rn(sum, xrow));
 }
@@ -614,7 +625,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   __shared__ Tile s_tile[kStages];
   __shared__ uint32_t s_tidx[kStages];              // index of the staged tile (dynamic schedule: its partial's slot)
   __shared__ double s_wdot[2][kWarps];              // dynamic schedule: the warps' dot() partials of a tile
-  __shared__ uint32_t s_crc[(MODE == ABFT_MODE_CRC32C) ? kCrcTabWords : 1];
+  __shared__ uint32_t s_crc[((MODE & 7) == ABFT_MODE_CRC32C) ? kCrcTabWords : 1];
   __shared__ double s_warp[kWarps];
 
   if (active && *active == 0) return;  // device-resident loop already converged
@@ -649,7 +660,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
   }
   __syncthreads();
   if (tid == 0) fence_proxy_async();
-  if (MODE == ABFT_MODE_CRC32C)
+  if ((MODE & 7) == ABFT_MODE_CRC32C)
     for (int i = tid; i < kCrcTabWords; i += BLOCK) s_crc[i] = g_crc5_tab[i];
   __syncthreads();
   // (Tried in round 2 and removed: launching this kernel as a programmatic dependent of calc_p, so that the set-up above
@@ -743,7 +754,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     mbar_wait(&s_full[st], (it / kStages) & 1u);
     const Tile t = s_tile[st];  // (written by thread 0 before it armed the barrier)
     if (DYN && t.info == kTileNone) break;
-    const bool irregular_tile = !(t.info & (kTileLongRow | kTileRegular)) && MODE != ABFT_MODE_CRC32C;
+    const bool irregular_tile = !(t.info & (kTileLongRow | kTileRegular)) && (MODE & 7) != ABFT_MODE_CRC32C;
     const StageBuf &B = stage[st];
     if (dynamic) dot_part = 0.0;  // reduced per tile below
     const uint32_t nrows = t.info & 0xFFFFu;
@@ -760,7 +771,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
       // reference's row checks and, when they pass, its walk over [start, end) from global memory -- one by one,
       // in its order (rare: a corrupted rows[]).  Uniform over the CTA (every thread reads the same two words).
       bool moved = false;
-      if (MODE == ABFT_MODE_CONSTRAINTS) {
+      if ((MODE & 7) == ABFT_MODE_CONSTRAINTS) {
         const uint32_t prs = B.rptr[t.row_begin - rb], pre = B.rptr[t.row_begin + 1 - rb];
         moved = prs != t.nnz_begin || pre != t.nnz_end;
         if (moved && tid == 0) {
@@ -787,7 +798,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           cw[k] = ld_stream(A.cols + li[k]);
           val[k] = ld_stream(A.values + li[k]);
         }
-        if (MODE == ABFT_MODE_CONSTRAINTS && !flagged) {
+        if ((MODE & 7) == ABFT_MODE_CONSTRAINTS && !flagged) {
 #pragma unroll
           for (int k = 0; k < kLongBatch; k++)
             if (ok[k] && !flagged) {
@@ -800,7 +811,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         for (int k = 0; k < kLongBatch; k++)
           if (ok[k]) acc = __dadd_rn(acc, pr[k]);
       }
-      if (MODE == ABFT_MODE_CRC32C && tid == 0) {
+      if ((MODE & 7) == ABFT_MODE_CRC32C && tid == 0) {
         // long rows are rare: one thread walks the row for the CRC
         uint32_t crc = 0xFFFFFFFFu, stored = 0;
         for (uint32_t e = 0; e < n; e++) {
@@ -813,10 +824,15 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         }
         if ((crc ^ 0xFFFFFFFFu) != stored) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + t.row_begin, 0);
       }
-      const double total = block_sum<BLOCK>(acc, s_warp);
+      double total = block_sum<BLOCK>(acc, s_warp);
       if (tid == 0) {
+        const double xr = x[A.row_offset + t.row_begin];
+        if (ModeTraits<MODE>::vec_sed) {
+          if (vec_parity_bits(xr) & 1u) log_event(L, ABFT_EV_VECTOR_SED, A.row_offset + t.row_begin, VEC_SPMV_OPERAND);
+          total = vec_encode(total);
+        }
         y[t.row_begin] = total;
-        dot_part = __dadd_rn(dot_part, __dmul_rn(total, x[A.row_offset + t.row_begin]));
+        dot_part = __dadd_rn(dot_part, __dmul_rn(total, xr));
       }
     } else {
       const bool irregular = irregular_tile;
@@ -865,7 +881,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         if (has_q) {
           rs = B.rptr[qrow - rb];
           re = B.rptr[qrow + 1 - rb];
-          if (MODE != ABFT_MODE_CONSTRAINTS) {
+          if ((MODE & 7) != ABFT_MODE_CONSTRAINTS) {
             // these modes trust rows[] like the reference; clamp so a bad pointer cannot fault
             rs = min(max(rs, t.nnz_begin), t.nnz_end);
             re = min(max(re, rs), t.nnz_end);
@@ -877,7 +893,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         const bool is_long = has_q && in_window && (re - rs > kSeqRowMax);
         double sum = 0.0;
         if (has_q && !is_long) {
-          if (MODE == ABFT_MODE_CONSTRAINTS) {
+          if ((MODE & 7) == ABFT_MODE_CONSTRAINTS) {
             bool bad = !in_window;
             if (!bad)
               for (uint32_t i = rs; i < re; i++) {
@@ -902,7 +918,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           double part = 0.0;
           bool bad = false;
           for (uint32_t i = ls + lane; i < le; i += 32) {
-            if (MODE == ABFT_MODE_CONSTRAINTS) {
+            if ((MODE & 7) == ABFT_MODE_CONSTRAINTS) {
               // CSR/CPUContext.cpp:188-200; a violation sends the whole row down the careful path
               const uint32_t c = B.cols[i - cb];
               bad |= (c >= A.n_cols);
@@ -912,10 +928,14 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
           }
           part = warp_sum(part);
           part = __shfl_sync(0xffffffffu, part, 0);
-          const bool any_bad = (MODE == ABFT_MODE_CONSTRAINTS) && __any_sync(0xffffffffu, bad);
+          const bool any_bad = ((MODE & 7) == ABFT_MODE_CONSTRAINTS) && __any_sync(0xffffffffu, bad);
           if (lane == src) sum = any_bad ? constraints_careful(qrow, rs, re) : part;
         }
         if (has_q) {
+          if (ModeTraits<MODE>::vec_sed) {
+            if (vec_parity_bits(xq) & 1u) log_event(L, ABFT_EV_VECTOR_SED, A.row_offset + qrow, VEC_SPMV_OPERAND);
+            sum = vec_encode(sum);
+          }
           y[qrow] = sum;
           dot_part = __dadd_rn(dot_part, __dmul_rn(sum, xq));
         }

@@ -11,6 +11,7 @@
 // from device slots (the device-resident loop, abft_cuda_cg_solve).
 #pragma once
 #include "common.cuh"
+#include "ecc.cuh"
 
 namespace abft {
 
@@ -20,6 +21,15 @@ struct ScalarArg {
   const double *den;
 };
 
+// VSED (mode secdedv, ecc.cuh): every element read is parity-checked (an odd one is reported: detect-only, fatal) and
+// every element written carries its parity in the lowest mantissa bit.  `which` names the vector in the report.
+template <bool VSED>
+__device__ __forceinline__ void vchk(double v, int index, int which, const LogRef &L) {
+  if (VSED && (vec_parity_bits(v) & 1u)) log_event(L, ABFT_EV_VECTOR_SED, (uint32_t)index, (uint32_t)which);
+}
+template <bool VSED>
+__device__ __forceinline__ double venc(double v) { return VSED ? vec_encode(v) : v; }
+
 template <bool DEV>
 __device__ __forceinline__ double scalar_of(const ScalarArg &s) {
   if (DEV) return __ddiv_rn(*s.num, *s.den);
@@ -28,8 +38,9 @@ __device__ __forceinline__ double scalar_of(const ScalarArg &s) {
 
 // grid-stride over pairs of doubles (128-bit accesses) when the pointers allow it;
 // the odd tail, or everything when a pointer is only 8-byte aligned, goes scalar
+template <bool VSED>
 __global__ void __launch_bounds__(kBlock) dot_kernel(const double *__restrict__ a, const double *__restrict__ b, int N,
-                                                      int vec_ok, ReduceOut red, const int *__restrict__ active) {
+                                                      int vec_ok, ReduceOut red, const int *__restrict__ active, LogRef L) {
   __shared__ double s_warp[kBlock / 32];
   if (active && *active == 0) return;
   const int n2 = vec_ok ? (N >> 1) : 0;  // vec_ok: every pointer is 16-byte aligned
@@ -38,21 +49,25 @@ __global__ void __launch_bounds__(kBlock) dot_kernel(const double *__restrict__ 
   double acc = 0.0;
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n2; i += gridDim.x * kBlock) {
     const double2 u = a2[i], v = b2[i];
+    vchk<VSED>(u.x, 2 * i, VEC_DOT_A, L); vchk<VSED>(u.y, 2 * i + 1, VEC_DOT_A, L);
+    vchk<VSED>(v.x, 2 * i, VEC_DOT_B, L); vchk<VSED>(v.y, 2 * i + 1, VEC_DOT_B, L);
     acc = __dadd_rn(acc, __dmul_rn(u.x, v.x));
     acc = __dadd_rn(acc, __dmul_rn(u.y, v.y));
   }
-  for (int i = 2 * n2 + blockIdx.x * kBlock + threadIdx.x; i < N; i += gridDim.x * kBlock)
+  for (int i = 2 * n2 + blockIdx.x * kBlock + threadIdx.x; i < N; i += gridDim.x * kBlock) {
+    vchk<VSED>(a[i], i, VEC_DOT_A, L); vchk<VSED>(b[i], i, VEC_DOT_B, L);
     acc = __dadd_rn(acc, __dmul_rn(a[i], b[i]));
+  }
   const double mine = block_sum(acc, s_warp);
   grid_sum_finalize(mine, red, s_warp);
 }
 
 // x += alpha p ; r -= alpha w ; sum r^2     (one pass: 32 B read + 16 B written per row)
-template <bool DEV>
+template <bool DEV, bool VSED>
 __global__ void __launch_bounds__(kBlock)
 calc_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
                const double *__restrict__ w, ScalarArg alpha_arg, int N, int vec_ok, ReduceOut red,
-               const int *__restrict__ active) {
+               const int *__restrict__ active, LogRef L) {
   __shared__ double s_warp[kBlock / 32];
   if (active && *active == 0) {
     // converged: this iteration is a no-op, and so is the next one
@@ -78,18 +93,27 @@ calc_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__r
       // L2 (evict-first) so that r and p, which calc_p and the next spmv want, stay
       double2 xv = __ldcs(x2 + i), rv = r2[i];
       const double2 pv = p2[i], wv = __ldcs(w2 + i);
-      xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
-      xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
-      rv.x = __dsub_rn(rv.x, __dmul_rn(alpha, wv.x));
-      rv.y = __dsub_rn(rv.y, __dmul_rn(alpha, wv.y));
+      if (VSED) {
+        vchk<VSED>(xv.x, 2 * i, VEC_X, L); vchk<VSED>(xv.y, 2 * i + 1, VEC_X, L);
+        vchk<VSED>(rv.x, 2 * i, VEC_R, L); vchk<VSED>(rv.y, 2 * i + 1, VEC_R, L);
+        vchk<VSED>(pv.x, 2 * i, VEC_P, L); vchk<VSED>(pv.y, 2 * i + 1, VEC_P, L);
+        vchk<VSED>(wv.x, 2 * i, VEC_W, L); vchk<VSED>(wv.y, 2 * i + 1, VEC_W, L);
+      }
+      xv.x = venc<VSED>(__dadd_rn(xv.x, __dmul_rn(alpha, pv.x)));
+      xv.y = venc<VSED>(__dadd_rn(xv.y, __dmul_rn(alpha, pv.y)));
+      rv.x = venc<VSED>(__dsub_rn(rv.x, __dmul_rn(alpha, wv.x)));
+      rv.y = venc<VSED>(__dsub_rn(rv.y, __dmul_rn(alpha, wv.y)));
       __stcs(x2 + i, xv);
       r2[i] = rv;
       acc = __dadd_rn(acc, __dmul_rn(rv.x, rv.x));
       acc = __dadd_rn(acc, __dmul_rn(rv.y, rv.y));
     }
   for (int i = 2 * n2 + blockIdx.x * kBlock + threadIdx.x; i < N; i += gridDim.x * kBlock) {
-    const double xn = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
-    const double rn = __dsub_rn(r[i], __dmul_rn(alpha, w[i]));
+    if (VSED) {
+      vchk<VSED>(x[i], i, VEC_X, L); vchk<VSED>(r[i], i, VEC_R, L); vchk<VSED>(p[i], i, VEC_P, L); vchk<VSED>(w[i], i, VEC_W, L);
+    }
+    const double xn = venc<VSED>(__dadd_rn(x[i], __dmul_rn(alpha, p[i])));
+    const double rn = venc<VSED>(__dsub_rn(r[i], __dmul_rn(alpha, w[i])));
     x[i] = xn;
     r[i] = rn;
     acc = __dadd_rn(acc, __dmul_rn(rn, rn));
@@ -99,10 +123,10 @@ calc_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__r
 }
 
 // p = r + beta p      (16 B read + 8 B written per row)
-template <bool DEV>
+template <bool DEV, bool VSED>
 __global__ void __launch_bounds__(kBlock)
 calc_p_kernel(double *__restrict__ p, const double *__restrict__ r, ScalarArg beta_arg, int N, int vec_ok,
-              const int *__restrict__ active) {
+              const int *__restrict__ active, LogRef L) {
   if (active && *active == 0) return;
   const double beta = scalar_of<DEV>(beta_arg);
   const int n2 = vec_ok ? (N >> 1) : 0;
@@ -111,12 +135,27 @@ calc_p_kernel(double *__restrict__ p, const double *__restrict__ r, ScalarArg be
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n2; i += gridDim.x * kBlock) {
     double2 pv = p2[i];
     const double2 rv = r2[i];
-    pv.x = __dadd_rn(rv.x, __dmul_rn(beta, pv.x));
-    pv.y = __dadd_rn(rv.y, __dmul_rn(beta, pv.y));
+    if (VSED) {
+      vchk<VSED>(pv.x, 2 * i, VEC_P, L); vchk<VSED>(pv.y, 2 * i + 1, VEC_P, L);
+      vchk<VSED>(rv.x, 2 * i, VEC_R, L); vchk<VSED>(rv.y, 2 * i + 1, VEC_R, L);
+    }
+    pv.x = venc<VSED>(__dadd_rn(rv.x, __dmul_rn(beta, pv.x)));
+    pv.y = venc<VSED>(__dadd_rn(rv.y, __dmul_rn(beta, pv.y)));
     p2[i] = pv;
   }
-  for (int i = 2 * n2 + blockIdx.x * kBlock + threadIdx.x; i < N; i += gridDim.x * kBlock)
-    p[i] = __dadd_rn(r[i], __dmul_rn(beta, p[i]));
+  for (int i = 2 * n2 + blockIdx.x * kBlock + threadIdx.x; i < N; i += gridDim.x * kBlock) {
+    if (VSED) { vchk<VSED>(p[i], i, VEC_P, L); vchk<VSED>(r[i], i, VEC_R, L); }
+    p[i] = venc<VSED>(__dadd_rn(r[i], __dmul_rn(beta, p[i])));
+  }
+}
+
+// mode secdedv, host -> device: give every element of a freshly uploaded vector its parity bit (unmap_vector) ...
+__global__ void __launch_bounds__(kBlock) vec_encode_kernel(double *__restrict__ v, int N) {
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < N; i += gridDim.x * kBlock) v[i] = vec_encode(v[i]);
+}
+// ... and device -> host: check a vector that is about to be mapped (map_vector)
+__global__ void __launch_bounds__(kBlock) vec_check_kernel(const double *__restrict__ v, int N, LogRef L) {
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < N; i += gridDim.x * kBlock) vchk<true>(v[i], i, VEC_MAPPED, L);
 }
 
 // ---- multi-GPU: p = r + beta p fused with the PUSH of the freshly computed entries into the
@@ -133,10 +172,10 @@ struct PushPlan {
   unsigned long long *phase;  // this iteration's row of phase stamps (null: off)
 };
 
-template <bool DEV, bool COMPUTE>
+template <bool DEV, bool COMPUTE, bool VSED>
 __global__ void __launch_bounds__(kBlock)
 calc_p_push_kernel(double *__restrict__ p, const double *__restrict__ r, ScalarArg beta_arg, int N, PushPlan plan,
-                   const int *__restrict__ active) {
+                   const int *__restrict__ active, LogRef L) {
   if (active && *active == 0) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) phase_stamp(plan.phase, PH_P_BEGIN);
   const double beta = COMPUTE ? scalar_of<DEV>(beta_arg) : 0.0;
@@ -150,7 +189,8 @@ calc_p_push_kernel(double *__restrict__ p, const double *__restrict__ r, ScalarA
       v[u] = 0.0;
       if (i < N) {
         if (COMPUTE) {
-          v[u] = __dadd_rn(r[i], __dmul_rn(beta, p[i]));
+          if (VSED) { vchk<VSED>(p[i], (int)i, VEC_P, L); vchk<VSED>(r[i], (int)i, VEC_R, L); }
+          v[u] = venc<VSED>(__dadd_rn(r[i], __dmul_rn(beta, p[i])));
           p[i] = v[u];
         } else {
           v[u] = p[i];

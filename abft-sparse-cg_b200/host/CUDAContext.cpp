@@ -97,6 +97,7 @@ class CUDAContext : public CGContext {
     for (int k = 1; k < G; k++) {
       long long e = (long long)nnz * k / G;
       int row = (e < nnz) ? (int)rows[e] : N;
+      if (MODE == ABFT_MODE_SECDEDV) row &= ~1;  // protected row pointers are coded in pairs: blocks start on even rows
       if (row < cut[k - 1]) row = cut[k - 1];
       cut[k] = row;
       long long lo = off[k - 1], hi = nnz;  // first element whose row >= cut[k]
@@ -368,5 +369,7 @@ static CGContext::Register<CUDAContext<ABFT_MODE_SEC7> > D("cuda", "sec7");
 static CGContext::Register<CUDAContext<ABFT_MODE_SEC8> > E("cuda", "sec8");
 static CGContext::Register<CUDAContext<ABFT_MODE_SECDED> > F("cuda", "secded");
 static CGContext::Register<CUDAContext<ABFT_MODE_CRC32C> > H("cuda", "crc32c");
+// secded + row pointers (SECDED per pair) + vectors (parity bit per element): what the reference leaves unprotected
+static CGContext::Register<CUDAContext<ABFT_MODE_SECDEDV> > I("cuda", "secdedv");
 
 }  // namespace

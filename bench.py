@@ -232,7 +232,7 @@ def cpu_reference_run(args, mode, t, b, iters, warm, check_iters=0):
         # oracle/_ref (the reference built from its own sources) did not travel: the oracle's C port of the same
         # algorithm -- serial, so it understates what the reference's OpenMP spmv would do
         t0 = time.time()
-        om = O.OracleMatrix(mode, t.cols, t.rows, t.vals, N)
+        om = O.OracleMatrix(mode if mode != "secdedv" else "secded", t.cols, t.rows, t.vals, N)
         t_create = time.time() - t0
         L = O.lib()
         x = np.zeros(N); r = b.copy(); p = b.copy(); w = np.zeros(N)
@@ -258,7 +258,8 @@ def cpu_reference_run(args, mode, t, b, iters, warm, check_iters=0):
         dt = time.time() - t0
         return dict(it_s=iters / dt, seconds=dt, create_s=t_create, kind="port", threads=1, check=check,
                     rr_after={"iterations": warm + iters, "rr": st["rr"]})
-    rc = O.RefContext(mode if mode != "crc32c" else "secded")   # (the reference has no crc32c: its costliest mode stands in)
+    ref_mode = mode if mode in ("none", "constraints", "sed", "sec7", "sec8", "secded") else "secded"
+    rc = O.RefContext(ref_mode)   # (the reference has no crc32c / secdedv: its costliest mode stands in)
     threads = omp_threads(ncpu)
     t0 = time.time()
     rc.create_matrix(t.cols, t.rows, t.vals, N)
@@ -506,7 +507,7 @@ def main():
                 "details": {"omp_threads": res["threads"], "host_cpus": os.cpu_count(),
                             "note": "reference cg-csr CPU target (CSR/CPUContext.cpp) through its CGContext API, OpenMP over "
                                     "all host cores (only spmv is parallel in the reference)"
-                                    + ("; the reference has no crc32c mode: secded stands in" if args.mode == "crc32c" else "")}}
+                                    + ("; the reference has no %s mode: secded stands in" % args.mode if args.mode in ("crc32c", "secdedv") else "")}}
         emit(line)
         return
 

@@ -41,7 +41,11 @@ enum abft_mode {
   ABFT_MODE_SEC8 = 4,
   ABFT_MODE_SECDED = 5,
   ABFT_MODE_CRC32C = 6,
-  ABFT_MODE_COUNT = 7
+  /* secded + what the reference leaves unprotected (CSR/CPUContext.cpp:54-113,123-124; repository-defined, DESIGN.md
+   * 9c/9d): the row pointers carry a SECDED code per pair, and every element of every vector a parity bit in place
+   * of its mantissa's least significant bit (detect-only: "[ECC] error detected in vector ..." + exit(1)). */
+  ABFT_MODE_SECDEDV = 7,
+  ABFT_MODE_COUNT = 8
 };
 
 /* One record per message the reference printf()s from inside spmv
@@ -61,7 +65,10 @@ enum abft_event_kind {
   ABFT_EV_ROWPTR_DOUBLE = 11,    /* "[ROWS] double-bit error detected in row pointer pair %d" fatal */
   /* more faults in one spmv than the device log holds (16384): the records past that were dropped, so the lines
    * printed can no longer equal the reference's -- reported last and fatal instead of silently; index = records dropped */
-  ABFT_EV_LOG_OVERFLOW = 12      /* "fault log overflow: %d events dropped"                 fatal */
+  ABFT_EV_LOG_OVERFLOW = 12,     /* "fault log overflow: %d events dropped"                 fatal */
+  /* mode secdedv: odd parity in a vector element; index = element (the column for spmv's operand), bit = which
+   * vector: 1 spmv operand, 2 x, 3 r, 4 p, 5 w, 6/7 dot operands, 8 a vector being mapped to the host */
+  ABFT_EV_VECTOR_SED = 13        /* "[ECC] error detected in vector %s at index %d"         fatal */
 };
 
 typedef struct abft_event {
@@ -145,6 +152,8 @@ abft_vector *abft_cuda_vector_wrap(abft_ctx *ctx, double *dev_ptr, int N);
 /* non-owning window [offset, offset+N) of another vector */
 abft_vector *abft_cuda_vector_view(abft_ctx *ctx, abft_vector *parent, int offset, int N);
 void abft_cuda_vector_destroy(abft_ctx *ctx, abft_vector *v);
+/* Injection aid for mode secdedv (the reference injects into the matrix only): flip bit 0..63 of element `index`. */
+int abft_cuda_vector_flip_bit(abft_ctx *ctx, abft_vector *vec, int index, int bit);
 int abft_cuda_vector_len(const abft_vector *v);
 double *abft_cuda_vector_dev_ptr(abft_vector *v);
 /* map_vector: device->host copy into a pinned staging buffer owned by the

@@ -111,9 +111,10 @@ void *emu_create_part(int mode, const uint32_t *cols, const uint32_t *coo_rows, 
   e->smem = (unsigned char *)aligned_alloc(128, (std::max(SpmvCfg<true>::dyn_smem, SpmvCfg<false>::dyn_smem) + 127) / 128 * 128);
   fill_crc_tables();
   emu::launch(2, kBlock, [&] { rowptr_kernel(coo_rows, (uint32_t)nnz, (uint32_t)N, (uint32_t)row_offset, e->rowptr.data()); });
-  if (mode >= ABFT_MODE_SED && mode <= ABFT_MODE_SECDED && nnz > 0)
-    emu::launch(2, kBlock, [&] { encode_elements_kernel(mode, e->cols.data(), e->vals.data(), (uint32_t)nnz); });
-  else if (mode == ABFT_MODE_CRC32C && N > 0)
+  const int base = mode == ABFT_MODE_SECDEDV ? ABFT_MODE_SECDED : mode;
+  if (base >= ABFT_MODE_SED && base <= ABFT_MODE_SECDED && nnz > 0)
+    emu::launch(2, kBlock, [&] { encode_elements_kernel(base, e->cols.data(), e->vals.data(), (uint32_t)nnz); });
+  else if (base == ABFT_MODE_CRC32C && N > 0)
     emu::launch(2, kBlock, [&] { encode_crc_rows_kernel(e->rowptr.data(), e->cols.data(), e->vals.data(), (uint32_t)N); });
   return e;
 }
@@ -170,6 +171,7 @@ int emu_spmv(void *h, const double *vec, double *result, abft_event *out, int ca
     case ABFT_MODE_SEC8: spmv_mode<ABFT_MODE_SEC8>(e, vec, result); break;
     case ABFT_MODE_SECDED: spmv_mode<ABFT_MODE_SECDED>(e, vec, result); break;
     case ABFT_MODE_CRC32C: spmv_mode<ABFT_MODE_CRC32C>(e, vec, result); break;
+    case ABFT_MODE_SECDEDV: spmv_mode<ABFT_MODE_SECDED | kVecSed>(e, vec, result); break;
     default: return -1;
   }
   *dot_out = e->scal_host;
@@ -180,21 +182,40 @@ int emu_spmv(void *h, const double *vec, double *result, abft_event *out, int ca
   return n;
 }
 
-// the vector kernels through the same machinery (host-scalar flavour)
+// the vector kernels through the same machinery (host-scalar flavour); mode secdedv: with the vectors' parity bit.
+// Fault records of these kernels are left in the log for emu_vec_events.
+static bool vsed_of(Emu *e) { return e->mode == ABFT_MODE_SECDEDV; }
 double emu_dot(void *h, const double *a, const double *b, int N, int grid) {
   Emu *e = (Emu *)h;
   const ReduceOut red = reduce_of(e);
-  emu::launch(grid, kBlock, [&] { dot_kernel(a, b, N, 1, red, nullptr); });
+  LogRef L{&e->log, &e->flag};
+  if (vsed_of(e)) emu::launch(grid, kBlock, [&] { dot_kernel<true>(a, b, N, 1, red, nullptr, L); });
+  else emu::launch(grid, kBlock, [&] { dot_kernel<false>(a, b, N, 1, red, nullptr, L); });
   return e->scal_host;
 }
 double emu_calc_xr(void *h, double *x, double *r, const double *p, const double *w, double alpha, int N, int grid) {
   Emu *e = (Emu *)h;
   const ReduceOut red = reduce_of(e);
-  emu::launch(grid, kBlock, [&] { calc_xr_kernel<false>(x, r, p, w, ScalarArg{alpha, nullptr, nullptr}, N, 1, red, nullptr); });
+  LogRef L{&e->log, &e->flag};
+  if (vsed_of(e)) emu::launch(grid, kBlock, [&] { calc_xr_kernel<false, true>(x, r, p, w, ScalarArg{alpha, nullptr, nullptr}, N, 1, red, nullptr, L); });
+  else emu::launch(grid, kBlock, [&] { calc_xr_kernel<false, false>(x, r, p, w, ScalarArg{alpha, nullptr, nullptr}, N, 1, red, nullptr, L); });
   return e->scal_host;
 }
-void emu_calc_p(double *p, const double *r, double beta, int N, int grid) {
-  emu::launch(grid, kBlock, [&] { calc_p_kernel<false>(p, r, ScalarArg{beta, nullptr, nullptr}, N, 1, nullptr); });
+void emu_calc_p(void *h, double *p, const double *r, double beta, int N, int grid) {
+  Emu *e = (Emu *)h;
+  LogRef L{&e->log, &e->flag};
+  if (vsed_of(e)) emu::launch(grid, kBlock, [&] { calc_p_kernel<false, true>(p, r, ScalarArg{beta, nullptr, nullptr}, N, 1, nullptr, L); });
+  else emu::launch(grid, kBlock, [&] { calc_p_kernel<false, false>(p, r, ScalarArg{beta, nullptr, nullptr}, N, 1, nullptr, L); });
+}
+void emu_vec_encode(double *v, int N) { emu::launch(2, kBlock, [&] { vec_encode_kernel(v, N); }); }
+// raw records the vector kernels logged since the last spmv / emu_vec_events
+int emu_vec_events(void *h, abft_event *out, int cap) {
+  Emu *e = (Emu *)h;
+  const int n = (int)std::min<unsigned>(e->log.count, (unsigned)std::min(cap, kLogCap));
+  for (int i = 0; i < n; i++) out[i] = e->log.ev[i];
+  e->log.count = 0;
+  e->flag = 0;
+  return n;
 }
 
 }  // extern "C"

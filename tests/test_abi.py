@@ -34,10 +34,11 @@ def test_exports_every_declared_symbol(pkg):
 def test_mode_names_are_the_reference_registrations(pkg):
     # lower-case, exact strcmp (CGContext.cpp:14; CSR/CPUContext.cpp:415-420); no '-' (run_tests:12-13)
     L = pkg.capi.load()
-    names = [L.abft_cuda_mode_name(i).decode() for i in range(7)]
-    assert names == ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"]
+    names = [L.abft_cuda_mode_name(i).decode() for i in range(8)]
+    # (the first six are the reference's; crc32c and secdedv are this repository's own modes)
+    assert names == ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c", "secdedv"]
     assert all("-" not in n and n == n.lower() for n in names)
-    assert L.abft_cuda_mode_name(7) is None and L.abft_cuda_mode_from_name(b"SECDED") == -1
+    assert L.abft_cuda_mode_name(8) is None and L.abft_cuda_mode_from_name(b"SECDED") == -1
     for i, n in enumerate(names):
         assert L.abft_cuda_mode_from_name(n.encode()) == i
 

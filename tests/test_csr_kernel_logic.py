@@ -17,8 +17,8 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"]
-FATAL = {1, 4, 5, 6, 7, 8, 9, 11}      # every kind but CORRECTED_BIT (2), CORRECTED_PARITY (3), ROWPTR_CORRECTED (10)
+MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded", "crc32c"]   # (secdedv = index 7: tests/test_vector_protection.py)
+FATAL = {1, 4, 5, 6, 7, 8, 9, 11, 12, 13}   # every kind but CORRECTED_BIT (2), CORRECTED_PARITY (3), ROWPTR_CORRECTED (10)
 ROWPTR_EVENTS = {10, 11}               # reported ahead of everything else, by pair (csrc/rowsecc.cuh)
 ROW_EVENTS = {5, 6, 9}                 # ROW_SIZE, ROW_ORDER, CRC_ROW
 REGULAR = 1 << 16
@@ -55,7 +55,10 @@ def _build(tmp, name, flags):
     L.emu_dot.argtypes = [C.c_void_p, f64p, f64p, C.c_int, C.c_int]
     L.emu_calc_xr.restype = C.c_double
     L.emu_calc_xr.argtypes = [C.c_void_p, f64p, f64p, f64p, f64p, C.c_double, C.c_int, C.c_int]
-    L.emu_calc_p.argtypes = [f64p, f64p, C.c_double, C.c_int, C.c_int]
+    L.emu_calc_p.argtypes = [C.c_void_p, f64p, f64p, C.c_double, C.c_int, C.c_int]
+    L.emu_vec_encode.argtypes = [f64p, C.c_int]
+    L.emu_vec_events.restype = C.c_int
+    L.emu_vec_events.argtypes = [C.c_void_p, C.POINTER(Event), C.c_int]
     return L
 
 
@@ -320,7 +323,7 @@ def test_vector_kernels(EMU, pkg, O, N):
     rr = EMU.emu_calc_xr(em.h, xe, re_, p, w, 0.37, N, grid)
     rr0 = L.orc_calc_xr(x2, r2, p, w, 0.37, N)
     assert np.array_equal(xe, x2) and np.array_equal(re_, r2) and abs(rr - rr0) <= 1e-12 * rr0
-    EMU.emu_calc_p(pe, re_, -1.25, N, grid)
+    EMU.emu_calc_p(em.h, pe, re_, -1.25, N, grid)
     L.orc_calc_p(p2, r2, -1.25, N)
     assert np.array_equal(pe, p2)
     em.close()
@@ -407,7 +410,7 @@ def test_cg_trajectory_with_the_emulated_kernels(EMU, pkg, O):
         assert not fatal
         lines += [O.format_event(*e) for e in events]
         rr_new = EMU.emu_calc_xr(em.h, x, r, p, w, rr / pw, N, 3)
-        EMU.emu_calc_p(p, r, rr_new / rr, N, 3)
+        EMU.emu_calc_p(em.h, p, r, rr_new / rr, N, 3)
         rr = rr_new
         hist.append(rr)
     assert lines == [O.format_event(*e) for e in ref["events"]] == ["[ECC] corrected bit 37 at index 1234"]

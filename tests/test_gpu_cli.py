@@ -105,7 +105,7 @@ def test_reference_run_tests_protocol(O, exe, mtx32):
     'double-bit error detected' under -x 2 (flaky by design when both flips hit the same bit, 1/96)."""
     code, text = O.run_cg_csr(exe, ["--list"])
     impls = [ln.strip() for ln in text.splitlines() if "-" in ln and ln.strip().startswith("cuda")]
-    assert len(impls) == 7
+    assert len(impls) == 8      # the reference's six modes + crc32c + secdedv
     base = ["-f", mtx32, "-b", "4"]
     for impl in impls:
         target, mode = impl.split("-")
