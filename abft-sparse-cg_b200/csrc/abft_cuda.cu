@@ -66,6 +66,7 @@ struct abft_matrix {
   unsigned int *d_tile_counter = nullptr;  // dynamic spmv schedule (matrices with irregular tiles)
   int n_tiles = 0;
   int64_t nnz_offset = 0;
+  int flen = 0;  // stencil matrix (static schedule, every tile regular): its longest row if that is 5 or 7, else 0
 };
 
 struct abft_ctx {
@@ -544,6 +545,17 @@ abft_matrix *abft_cuda_matrix_create_part(abft_ctx *c, const uint32_t *columns, 
   CKP(cudaMalloc(&m->d_tiles, sizeof(Tile) * (size_t)std::max(m->n_tiles, 1)));
   if (m->n_tiles)
     CKP(cudaMemcpy(m->d_tiles, tiles.data(), sizeof(Tile) * (size_t)m->n_tiles, cudaMemcpyHostToDevice));
+  if (kind == 0 && m->n_tiles > 0) {
+    // a stencil matrix?  (the stencil instantiations of spmv_kernel: 5- and 7-point rows, what BASELINE's configs are)
+    uint32_t longest = 0;
+    bool all_regular = true;
+    for (const Tile &t : tiles) {
+      all_regular &= (t.info & kTileRegular) != 0;
+      longest = std::max(longest, (t.info >> kTileMaxLenShift) & 0xFFFu);
+    }
+    const char *force = getenv("ABFT_CUDA_SPMV_KERNEL");   // test hook: "generic" keeps the general instantiation
+    if (all_regular && (longest == 5 || longest == 7) && !(force && !strcmp(force, "generic"))) m->flen = (int)longest;
+  }
   m->view.rowptr = m->d_rowptr;
   m->view.tiles = m->d_tiles;
   m->view.tile_counter = m->d_tile_counter;
@@ -785,11 +797,41 @@ static int spmv_resident_ctas(abft_ctx *c) {
   return cached * c->num_sms;
 }
 
+// persistent grid: SMs x resident CTAs of this mode's kernel (never more CTAs than tiles)
+template <int MODE, int FLEN>
+static int spmv_stencil_ctas(abft_ctx *c) {
+  static int cached[64] = {0};   // per device
+  int &v = cached[c->device & 63];
+  if (v == 0) {
+    const int smem = (int)SpmvCfg<false>::dyn_smem;
+    cudaFuncSetAttribute(spmv_kernel<MODE, false, FLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_kernel<MODE, false, FLEN>, SpmvCfg<false>::block, smem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    v = per_sm;
+  }
+  return v * c->num_sms;
+}
+
+template <int MODE, int FLEN>
+static void launch_spmv_stencil(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,
+                                const int *active, const WaitSpec &wait) {
+  LogRef L{c->d_log, c->h_flag};
+  const int grid = std::min(m->n_tiles, spmv_stencil_ctas<MODE, FLEN>(c));
+  spmv_kernel<MODE, false, FLEN><<<grid, SpmvCfg<false>::block, SpmvCfg<false>::dyn_smem, c->stream>>>(m->view, x, y, L, red, active, wait);
+}
+
 template <int MODE>
 static void launch_spmv_mode(abft_ctx *c, const abft_matrix *m, const double *x, double *y, const ReduceOut &red,
                              const int *active, const WaitSpec &wait) {
   LogRef L{c->d_log, c->h_flag};
-  if (m->view.tile_counter) {
+  // the compute-bound modes have stencil instantiations (the others run at the HBM roofline as they are)
+  constexpr bool has_stencil = (MODE & 7) == ABFT_MODE_SEC7 || (MODE & 7) == ABFT_MODE_SECDED || (MODE & 7) == ABFT_MODE_CRC32C;
+  if (has_stencil && m->flen == 7) {
+    launch_spmv_stencil<has_stencil ? MODE : ABFT_MODE_SECDED, 7>(c, m, x, y, red, active, wait);
+  } else if (has_stencil && m->flen == 5) {
+    launch_spmv_stencil<has_stencil ? MODE : ABFT_MODE_SECDED, 5>(c, m, x, y, red, active, wait);
+  } else if (m->view.tile_counter) {
     const int grid = std::min(m->n_tiles, spmv_resident_ctas<MODE, true>(c));
     spmv_kernel<MODE, true><<<grid, SpmvCfg<true>::block, SpmvCfg<true>::dyn_smem, c->stream>>>(m->view, x, y, L, red, active, wait);
   } else {

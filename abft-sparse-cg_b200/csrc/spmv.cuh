@@ -462,7 +462,11 @@ template <int BLOCK>
 __device__ __forceinline__ void rows_prepass(uint32_t *rp, const Tile &t, const MatView &A, const LogRef &L, int tid) {
   const uint32_t wb = t.row_begin & ~3u;
   const uint32_t n_words = ((t.row_begin + (t.info & 0xFFFFu) + 1 + 3) & ~3u) - wb;
-  for (uint32_t k = 2 * tid; k + 1 < n_words; k += 2 * BLOCK) {
+  // the UPPER half of the CTA's threads takes the pairs: thread 0's warp already runs the tile refill on top of its
+  // rows and is the one the per-tile barrier waits for
+  const int u = BLOCK >= 64 ? tid - BLOCK / 2 : tid;
+  if (u < 0) return;
+  for (uint32_t k = 2 * (uint32_t)u; k + 1 < n_words; k += (BLOCK >= 64 ? BLOCK : 2 * BLOCK)) {
     uint32_t w0 = rp[k], w1 = rp[k + 1], bit = 0;
     const int verdict = rows_check_pair(w0, w1, &bit);
     const uint32_t pair = (A.row_offset + wb + k) / 2;   // (partitions start on even rows when protected)
@@ -510,14 +514,16 @@ __device__ __forceinline__ double constraints_careful_row(uint32_t lrow, uint32_
 // One row of a regular tile per lane, straight from the staged stream (WARP-COLLECTIVE: every lane of the warp calls it,
 // lanes without a row with has_row = false).  `k` = the lane's row number inside the tile.  Writes y[row] and adds the
 // row's share of dot(vec, result) to dot_part.
-template <int MODE>
+// FLEN != 0: the matrix-wide longest row, fixed at compile time (the stencil instantiations of spmv_kernel): one unrolled
+// walk, no dispatch on the tile's own longest row.
+template <int MODE, int FLEN = 0>
 __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_row, const uint32_t *s_rptr,
                                             const uint32_t *s_cols, const double *s_vals, const MatView &A,
                                             const double *__restrict__ x, double *__restrict__ y, const LogRef &L,
                                             const uint32_t *s_crc, double &dot_part) {
   const uint32_t rb = t.row_begin & ~3u, cb = t.nnz_begin & ~3u, vb = t.nnz_begin & ~1u;
   const uint32_t row = t.row_begin + k;
-  const uint32_t max_len = (t.info >> kTileMaxLenShift) & 0xFFFu;  // uniform over the tile
+  const uint32_t max_len = FLEN ? (uint32_t)FLEN : ((t.info >> kTileMaxLenShift) & 0xFFFu);  // uniform over the tile
   const uint32_t need = max_len <= 4 ? 4u : max_len;               // the unrolled walk's length
   uint32_t rs = 0, re = 0;
   double xrow = 0.0;
@@ -548,6 +554,7 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
     // the window; the reference walks the whole [start, end) range (CSR/CPUContext.cpp:125,184), so such a
     // row goes down the one-by-one path instead of an unrolled walk that would stop after max_len elements.
     if (max_len <= 7 && len > need) suspect = 1u;
+    else if (FLEN) sum = walk_chunk<MODE, (FLEN >= 4 && FLEN <= 7) ? FLEN : 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
     else if (max_len <= 4) sum = walk_chunk<MODE, 4>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
     else if (max_len == 5) sum = walk_chunk<MODE, 5>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
     else if (max_len == 6) sum = walk_chunk<MODE, 6>(sum, 0, len, sc, sv, A.n_cols, x, suspect, full_rows);
@@ -561,7 +568,8 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
   }
   if ((MODE & 7) == ABFT_MODE_CRC32C && max_len <= 7 && len >= 4 && len <= need) {
     bool bad = false;
-    if (max_len <= 4) sum = walk_crc<4>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
+    if (FLEN) sum = walk_crc<(FLEN >= 4 && FLEN <= 7) ? FLEN : 4>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
+    else if (max_len <= 4) sum = walk_crc<4>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
     else if (max_len == 5) sum = walk_crc<5>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
     else if (max_len == 6) sum = walk_crc<6>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
     else sum = walk_crc<7>(len, sc, sv, A.n_cols, x, s_crc, full_rows, bad);
@@ -607,7 +615,11 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
 }
 
 // DYN: the dynamic tile schedule (A.tile_counter), compiled as its own kernel so that the static one carries none of it
-template <int MODE, bool DYN>
+// FLEN != 0 (static schedule only): a stencil matrix -- every tile regular, no row longer than FLEN (5 or 7) -- gets an
+// instantiation without the long-row and irregular-tile paths and with the row walk's length fixed: ~20 fewer
+// instructions per warp and tile of the ~100 that are not the walk itself (this kernel's time follows its instruction
+// count, see the notes at the refill below).
+template <int MODE, bool DYN, int FLEN = 0>
 __global__ void __launch_bounds__(SpmvCfg<DYN>::block, 4)
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
             const int *__restrict__ active, WaitSpec wait) {
@@ -754,7 +766,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     mbar_wait(&s_full[st], (it / kStages) & 1u);
     const Tile t = s_tile[st];  // (written by thread 0 before it armed the barrier)
     if (DYN && t.info == kTileNone) break;
-    const bool irregular_tile = !(t.info & (kTileLongRow | kTileRegular)) && (MODE & 7) != ABFT_MODE_CRC32C;
+    const bool irregular_tile = FLEN == 0 && !(t.info & (kTileLongRow | kTileRegular)) && (MODE & 7) != ABFT_MODE_CRC32C;
     const StageBuf &B = stage[st];
     if (dynamic) dot_part = 0.0;  // reduced per tile below
     const uint32_t nrows = t.info & 0xFFFFu;
@@ -762,7 +774,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
     const uint32_t rb = t.row_begin & ~3u, cb = t.nnz_begin & ~3u, vb = t.nnz_begin & ~1u;
     const bool has_row = (uint32_t)tid < nrows;
 
-    if (t.info & kTileLongRow) {
+    if (FLEN == 0 && (t.info & kTileLongRow)) {
       // ---------------- one long row: stream it from global memory in chunks ----------------
       double acc = 0.0;
       bool flagged = false;
@@ -941,7 +953,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         }
       } else {
         // ---------------- regular tile: thread-per-row straight from the staged stream ----------------
-        regular_row<MODE>(t, (uint32_t)tid, has_row, B.rptr, B.cols, B.vals, A, x, y, L, s_crc, dot_part);
+        regular_row<MODE, FLEN>(t, (uint32_t)tid, has_row, B.rptr, B.cols, B.vals, A, x, y, L, s_crc, dot_part);
       }
     }
     if (dynamic) {

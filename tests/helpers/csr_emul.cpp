@@ -21,6 +21,7 @@ struct Emu {
   std::vector<Tile> tiles;
   bool dyn = false;
   int kind = 0;  // abft_cuda_plan_matrix: 0 static round-robin, 1 dynamic schedule
+  int flen = 0;  // stencil matrix: its longest row if 5 or 7 (abft_cuda.cu picks the same instantiation)
   bool rows_ecc = false;
   unsigned int tile_counter = 0;
   DevLog log;
@@ -67,7 +68,13 @@ void spmv_inst(Emu *e, const double *vec, double *result) {
   LogRef L{&e->log, &e->flag};
   const ReduceOut red = reduce_of(e);
   const int grid = std::max(1, std::min((int)e->tiles.size(), e->grid));
-  emu::launch(grid, SpmvCfg<DYN>::block, [&] { spmv_kernel<MODE, DYN>(A, vec, result, L, red, nullptr, WaitSpec{nullptr, 0u, 0u}); });
+  constexpr bool has_stencil = !DYN && ((MODE & 7) == ABFT_MODE_SEC7 || (MODE & 7) == ABFT_MODE_SECDED || (MODE & 7) == ABFT_MODE_CRC32C);
+  if (has_stencil && e->flen == 7)
+    emu::launch(grid, SpmvCfg<false>::block, [&] { spmv_kernel<has_stencil ? MODE : ABFT_MODE_SECDED, false, 7>(A, vec, result, L, red, nullptr, WaitSpec{nullptr, 0u, 0u}); });
+  else if (has_stencil && e->flen == 5)
+    emu::launch(grid, SpmvCfg<false>::block, [&] { spmv_kernel<has_stencil ? MODE : ABFT_MODE_SECDED, false, 5>(A, vec, result, L, red, nullptr, WaitSpec{nullptr, 0u, 0u}); });
+  else
+    emu::launch(grid, SpmvCfg<DYN>::block, [&] { spmv_kernel<MODE, DYN>(A, vec, result, L, red, nullptr, WaitSpec{nullptr, 0u, 0u}); });
 }
 
 template <int MODE>
@@ -133,7 +140,18 @@ void emu_set_tiles(void *h, const uint32_t *recs, int n_tiles, int kind, int gri
   e->kind = kind;
   e->dyn = kind == 1;
   e->grid = grid;
+  e->flen = 0;
+  if (kind == 0 && n_tiles > 0) {   // the rule of abft_cuda_matrix_create_part
+    uint32_t longest = 0;
+    bool all_regular = true;
+    for (const Tile &t : e->tiles) {
+      all_regular &= (t.info & kTileRegular) != 0;
+      longest = std::max(longest, (t.info >> kTileMaxLenShift) & 0xFFFu);
+    }
+    if (all_regular && (longest == 5 || longest == 7) && !getenv("ABFT_EMU_GENERIC")) e->flen = (int)longest;
+  }
 }
+int emu_flen(void *h) { return ((Emu *)h)->flen; }
 
 // row-pointer protection (rowsecc.cuh), as abft_cuda_matrix_create_part applies it
 int emu_protect_rows(void *h) {

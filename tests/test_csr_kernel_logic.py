@@ -511,3 +511,15 @@ def test_edge_shapes(EMU, pkg, O, mode):
                     em.flip(index, 17)
                     om.flip(index, 17)
         em.close()
+
+
+def test_stencil_matrices_get_the_fixed_length_instantiation(EMU, pkg):
+    """5- and 7-point stencil matrices run spmv_kernel<MODE, false, FLEN> (row walk length fixed at compile time, no
+    long-row / irregular-tile paths); anything else keeps the general instantiation.  Every test of this file that uses
+    p3d_12 / p2d_40 in a compute-bound mode therefore exercises the stencil kernels, ragged / short_rows the general one."""
+    EMU.emu_flen.restype = C.c_int
+    EMU.emu_flen.argtypes = [C.c_void_p]
+    for name, want in (("p3d_12", 7), ("p2d_40", 5), ("p2d_12_b3", 5), ("ragged", 0), ("short_rows", 0), ("powerlaw", 0)):
+        em = EmuMatrix(EMU, pkg, "secded", shapes(pkg.matgen)[name]())
+        assert EMU.emu_flen(em.h) == want, name
+        em.close()

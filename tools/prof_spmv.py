@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--mode", default="secded")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--rows", type=int, default=1 << 21, help="powerlaw: N")
+    ap.add_argument("--nnz", type=int, default=50_000_000, help="powerlaw: target non-zeros")
     a = ap.parse_args()
     pkg = pkg_loader.load()
     mg = pkg.matgen
@@ -28,7 +30,7 @@ def main():
     elif a.workload == "poisson2d_blocks":
         t = mg.poisson2d(512, 64)
     else:
-        t = mg.powerlaw(1 << 21, 50_000_000, seed=1)
+        t = mg.powerlaw(a.rows, a.nnz, seed=1)
     ctx = pkg.CUDAContext(a.mode, 0)
     A = ctx.create_matrix(t.cols, t.rows, t.vals, t.N)
     p, w = ctx.create_vector(t.N), ctx.create_vector(t.N)
