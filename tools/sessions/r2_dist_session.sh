@@ -2,7 +2,7 @@
 # Multi-GPU GPU call (gpurun --gpus N): every multi-GPU test on all GPUs of the box, then the bench line at N
 # (plus N/2, N/4 ... when asked: SCALE="1 2 4 8"), with phase stamps of a short partitioned solve.
 set -uo pipefail
-ROOT="$(cd "$(dirname "$0")/.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 N=$(python -c "import torch; print(torch.cuda.device_count())")
 nvidia-smi --query-gpu=index,name,clocks.sm --format=csv,noheader | head -8

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # 2-GPU call: whole GPU suite (multi-GPU tests included), then N=1,2 with and without PDL, then phases.
 set -uo pipefail
-ROOT="$(cd "$(dirname "$0")/.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 N=$(python -c "import torch; print(torch.cuda.device_count())")
 timeout 1200 python -m pytest tests -q -m gpu > gpurun_out/r2d2_pytest_n$N.txt 2>&1; el "pytest -m gpu on $N GPUs rc=$?"; tail -5 gpurun_out/r2d2_pytest_n$N.txt

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Round-2 first GPU call (1 GPU): everything round 1 left unseen on hardware, then the kernel A/B.
 set -uo pipefail
-ROOT="$(cd "$(dirname "$0")/.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader
 timeout 900 python -m pytest tests -q -m gpu --durations=15 > gpurun_out/r2_pytest_gpu.txt 2>&1; el "pytest -m gpu rc=$?"; tail -25 gpurun_out/r2_pytest_gpu.txt
@@ -18,6 +18,6 @@ for v in crcwalk crc6 crcwalk6 crc5 crcwalk5_t1536; do ab $v crc32c; done
 ab rowsecc none,secded
 ab rowsecc none,secded ABFT_CUDA_PROTECT_ROWS=secded
 cat gpurun_out/r2_ab.jsonl | cut -c1-260
-timeout 600 tools/gpu_session.sh coo > gpurun_out/r2_coo.txt 2>&1; el "coo rc=$?"; tail -30 gpurun_out/r2_coo.txt | cut -c1-400
-timeout 600 tools/gpu_session.sh c5 > gpurun_out/r2_c5.txt 2>&1; el "c5 rc=$?"; cut -c1-1200 gpurun_out/r2_c5.txt
+timeout 600 tools/gpu_session.sh (round 1, removed) coo > gpurun_out/r2_coo.txt 2>&1; el "coo rc=$?"; tail -30 gpurun_out/r2_coo.txt | cut -c1-400
+timeout 600 tools/gpu_session.sh (round 1, removed) c5 > gpurun_out/r2_c5.txt 2>&1; el "c5 rc=$?"; cut -c1-1200 gpurun_out/r2_c5.txt
 timeout 400 python bench.py > gpurun_out/r2_bench0.json 2> gpurun_out/r2_bench0.err; el "bench rc=$?"; cut -c1-1500 gpurun_out/r2_bench0.json

@@ -2,7 +2,7 @@
 # Round-2 second GPU call (1 GPU): the rewritten spmv (block-size knob, uniform walk adopted, new CRC32C check, overlapped
 # row-pointer pre-pass) -- parity, A/B, ncu --set full of the two kernels that are below the bar, the new bench.py.
 set -uo pipefail
-ROOT="$(cd "$(dirname "$0")/.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_rowptr.py tests/test_gpu_fuzz.py tests/test_gpu_cli_coo.py -x -q -m gpu > gpurun_out/r2s2_pytest.txt 2>&1; el "pytest rc=$?"; tail -6 gpurun_out/r2s2_pytest.txt
 : > gpurun_out/r2s2_ab.jsonl

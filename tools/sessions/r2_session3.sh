@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Round-2 third GPU call (1 GPU): the warp-pipeline spmv kernel against the CTA-tiled one.
 set -uo pipefail
-ROOT="$(cd "$(dirname "$0")/.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2s3_pytest.txt 2>&1; el "pytest rc=$?"; tail -6 gpurun_out/r2s3_pytest.txt
 ABFT_CUDA_SPMV_KERNEL=cta timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_rowptr.py -x -q -m gpu > gpurun_out/r2s3_pytest_cta.txt 2>&1; el "pytest (cta kernel) rc=$?"; tail -3 gpurun_out/r2s3_pytest_cta.txt

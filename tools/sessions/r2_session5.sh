@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Round-2 fifth GPU call (1 GPU): everything green again after the revert; gathers-first / local-OR isolated.
 set -uo pipefail
-ROOT="$(cd "$(dirname "$0")/.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 timeout 900 python -m pytest tests -q -m gpu > gpurun_out/r2s5_pytest.txt 2>&1; el "pytest rc=$?"; tail -6 gpurun_out/r2s5_pytest.txt
 : > gpurun_out/r2s5_ab.jsonl

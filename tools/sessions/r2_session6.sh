@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Round-2 sixth 1-GPU call: mode secdedv on the device, the whole suite after the vector-kernel signature change, bench.
 set -uo pipefail
-ROOT="$(cd "$(dirname "$0")/.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 timeout 900 python -m pytest tests -q -m gpu > gpurun_out/r2s6_pytest.txt 2>&1; el "pytest rc=$?"; tail -8 gpurun_out/r2s6_pytest.txt
 timeout 500 python bench.py > gpurun_out/r2s6_bench.json 2> gpurun_out/r2s6_bench.err; el "bench rc=$?"; cut -c1-400 gpurun_out/r2s6_bench.json; tail -3 gpurun_out/r2s6_bench.err

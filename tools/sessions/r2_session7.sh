@@ -2,7 +2,7 @@
 # Round-2 seventh 1-GPU call (short): stencil instantiations vs the general kernel, row-pointer pre-pass on the upper
 # half of the CTA; ncu captures for the record (secded, crc32c on 256^3; sec7 on the power-law matrix at its named size).
 set -uo pipefail
-ROOT="$(cd "$(dirname "$0")/.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"; cd "$ROOT"; mkdir -p gpurun_out
 T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
 : > gpurun_out/r2s7_ab.jsonl
 ab() { local tag=$1 modes=$2; shift 2
