@@ -1317,7 +1317,10 @@ static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_v
   if (cudaSetDevice(c->device) != cudaSuccess) return -1;
   cudaStream_t s = c->stream;
   int *flag0 = c->d_loop, *iters = c->d_loop + 2;
-  cudaMemsetAsync(c->d_loop, 0, sizeof(int) * 4, s);
+  if (cudaMemsetAsync(c->d_loop, 0, sizeof(int) * 4, s) != cudaSuccess) {
+    fail(-1, "cg_solve: memset failed", __FILE__, __LINE__);
+    return -1;
+  }
   c->h_loop[0] = 0;
   c->h_loop[1] = 0;
   const unsigned int seq0 = m ? m->seq : 0u, epoch0 = m ? m->epoch : 0u;
@@ -1339,8 +1342,11 @@ static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_v
   const int push_grid = (int)std::max(1LL, std::min(want, (long long)c->num_sms * 8));
 
   // r = b ; p = r (+ exchange) ; rr = r.r   (cg.cpp:87-91)
-  cudaMemcpyAsync(r->d, b->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(p_local->d, r->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s);
+  if (cudaMemcpyAsync(r->d, b->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+      cudaMemcpyAsync(p_local->d, r->d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+    fail(-1, "cg_solve: device copy failed", __FILE__, __LINE__);
+    return -1;
+  }
   if (m) {
     PushPlan plan{};
     push_plan(plan);
@@ -1400,9 +1406,9 @@ static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_v
       }
     }
     // read back progress: iterations done and whether the next one would run
-    cudaMemcpyAsync(c->h_loop, c->d_loop + 2, sizeof(int), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(c->h_loop + 1, c->d_loop + (launched & 1), sizeof(int), cudaMemcpyDeviceToHost, s);
-    if (cudaStreamSynchronize(s) != cudaSuccess) {
+    if (cudaMemcpyAsync(c->h_loop, c->d_loop + 2, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(c->h_loop + 1, c->d_loop + (launched & 1), sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
       fail(-1, "cg_solve: stream sync failed", __FILE__, __LINE__);
       return -1;
     }
@@ -1436,6 +1442,9 @@ static int cg_solve_impl(abft_ctx *c, abft_comm *m, abft_matrix *A, const abft_v
   if (rr_out && cudaMemcpy(rr_out, c->d_scalars + ((done_iters & 1) ? SLOT_RR1 : SLOT_RR0), sizeof(double),
                            cudaMemcpyDeviceToHost) != cudaSuccess)
     return -1;
+  // a partitioned solve that saw a fatal fault on this rank ran on in lock-step with its peers (above); it still
+  // reports it: the reference would have exit(1)ed inside that spmv
+  if (fatal_seen) return -2;
   return done_iters;
 }
 

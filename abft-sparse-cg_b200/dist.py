@@ -173,6 +173,8 @@ class DistCG:
         it = self.L.abft_cuda_dist_cg_solve(self.ctx.ctx, self.comm, self.A.handle, self.b.handle, self.x.handle,
                                             self.r.handle, self.p.handle, self.p_full.handle, self.w.handle, int(max_itrs),
                                             float(conv), int(check_every), C.byref(rr))
+        if it == -2:
+            self.ctx.report_faults()     # a fatal fault on this rank: raises FatalFault with the lines the reference prints
         if it < 0:
             from . import capi
             raise RuntimeError("cuda target: dist_cg_solve failed: " + capi.last_error())

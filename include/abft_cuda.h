@@ -272,7 +272,8 @@ int abft_cuda_dist_calc_xr_async(abft_ctx *ctx, abft_comm *comm, abft_vector *x,
 
 /* device-resident loop over a row partition: like abft_cuda_cg_solve, every rank calls it with the same
  * arguments; scalars never visit the host, the exchange and the all-reduces stay inside the kernels.  A fatal
- * fault does not stop it early (ranks wait on each other): poll the events afterwards.  Returns iterations. */
+ * fault does not stop it early (the ranks wait on each other and must issue the same kernels); the rank that logged
+ * it returns -2 once the loop has run out (poll its events), the others their iteration count. */
 int abft_cuda_dist_cg_solve(abft_ctx *ctx, abft_comm *comm, abft_matrix *A, const abft_vector *b, abft_vector *x,
                             abft_vector *r, abft_vector *p_local, abft_vector *p_full, abft_vector *w, int max_itrs,
                             double conv_threshold, int check_every, double *rr_out);
