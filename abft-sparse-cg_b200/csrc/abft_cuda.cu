@@ -128,6 +128,10 @@ static int ensure_tables(int device) {
     for (int j = 0; j < kCrcChunks; j++)
       for (uint32_t cc = 0; cc < 32; cc++) tab5[(size_t)((m - 1) * kCrcChunks + j) * 32 + cc] = crc5_entry(m, j, cc);
   CK(cudaMemcpyToSymbol(g_crc5_tab, tab5.data(), sizeof(uint32_t) * (size_t)kCrcTabWords));
+  std::vector<uint32_t> tabe((size_t)kCrcElemChunks * 32);
+  for (int i = 0; i < kCrcElemChunks; i++)
+    for (uint32_t cc = 0; cc < 32; cc++) tabe[(size_t)i * 32 + cc] = crc_elem_entry(i, cc);
+  CK(cudaMemcpyToSymbol(g_crc_elem_tab, tabe.data(), sizeof(uint32_t) * tabe.size()));
   if (device >= 0 && device < 64) g_tables_ready[device] = true;
   return 0;
 }

@@ -144,4 +144,18 @@ constexpr uint32_t crc5_entry(int m, int j, uint32_t c) {   // (host side: libra
   return x;
 }
 
+// The same check with the chunks cut from the whole 88-bit element {state ^ w0, w1, col} instead of from each word:
+// 18 chunks instead of 7 + 7 + 5 (chunk 6 takes two bits of the first word and three of the second, chunk 12 four of
+// the second and one of the column).  Bit p of the element goes through F^3 (p < 32), F^2 (p < 64) or F (p < 88).
+constexpr int kCrcElemChunks = 18;
+constexpr uint32_t crc_elem_entry(int chunk, uint32_t c) {   // (host side: library init)
+  uint32_t r = 0;
+  for (int b = 0; b < 5; b++) {
+    const int p = 5 * chunk + b;
+    if (!((c >> b) & 1u) || p >= 88) continue;
+    const int m = p < 32 ? 3 : (p < 64 ? 2 : 1), bit = p & 31;   // (p - 64 == p & 31 for 64 <= p < 88)
+    r ^= crc5_entry(m, bit / 5, 1u << (bit % 5));
+  }
+  return r;
+}
 }  // namespace abft

@@ -387,6 +387,40 @@ __device__ __forceinline__ uint32_t crc_word(uint32_t crc, uint32_t w, const uin
   return tab[768 + (x & 0xFF)] ^ tab[512 + ((x >> 8) & 0xFF)] ^ tab[256 + ((x >> 16) & 0xFF)] ^ tab[x >> 24];
 }
 
+// ---- the same check with the tables in REGISTERS (stencil instantiations) ------------------------------------------
+// Shared-memory lookups, conflict-free or not, cost the data pipe one wavefront each and the ALU pipe a shift and a
+// mask to form the address; that pipe pair is what bounds the kernel above.  A 32-entry table is also one register
+// per lane -- lane c holds entry c -- and a lookup one SHFL.IDX whose lane operand is `x >> 5j` as it stands (the
+// instruction reads the low five bits only): no mask, no address, and for chunk 0 no shift.  The chunks are cut from
+// the whole 88-bit element {state ^ w0, w1, col} (ecc.cuh, crc_elem_entry): 18 lookups instead of 7 + 7 + 5, two
+// of them through a funnel shift across a word boundary.  The whole warp must walk in step.  256^3: 0.459 -> 0.405 ms
+// (profiles/r2_ab_session11_crc_register_tables.jsonl).  SHFL shares the data pipe with LDS (tools/microbench.cu:
+// together they issue at the rate of either), so the kernel stays bound by that pipe (82 % busy) next to the ALU pipe
+// (62 %); the last, three-bit chunk computed without a lookup (multiply, three PRMT sign masks, three LOP3) was slower.
+__device__ uint32_t g_crc_elem_tab[kCrcElemChunks * 32];  // [chunk][c], filled by the host at library init
+struct CrcRegs {
+  uint32_t t[kCrcElemChunks];
+};
+__device__ __forceinline__ void crc_regs_load(CrcRegs &cr, int lane) {
+#pragma unroll
+  for (int i = 0; i < kCrcElemChunks; i++) cr.t[i] = g_crc_elem_tab[i * 32 + lane];
+}
+#define ABFT_CRC_LOOKUP(i, idx) __shfl_sync(0xffffffffu, cr.t[i], (int)(idx))
+// the 11 lookups of an element that do not depend on the running state (bits 35..87: w1 from bit 3 on, and col)
+__device__ __forceinline__ uint32_t crc_elem_free(uint32_t w1, uint32_t colw, uint32_t col, const CrcRegs &cr) {
+  uint32_t r = ABFT_CRC_LOOKUP(7, w1 >> 3) ^ ABFT_CRC_LOOKUP(8, w1 >> 8) ^ ABFT_CRC_LOOKUP(9, w1 >> 13);
+  r ^= ABFT_CRC_LOOKUP(10, w1 >> 18) ^ ABFT_CRC_LOOKUP(11, w1 >> 23) ^ ABFT_CRC_LOOKUP(12, __funnelshift_r(w1, colw, 28));
+  // (colw = the stored column word, check byte and all: its bits above 23 never reach the low five of these four)
+  r ^= ABFT_CRC_LOOKUP(13, colw >> 1) ^ ABFT_CRC_LOOKUP(14, colw >> 6) ^ ABFT_CRC_LOOKUP(15, colw >> 11);
+  return r ^ ABFT_CRC_LOOKUP(16, colw >> 16) ^ ABFT_CRC_LOOKUP(17, col >> 21);
+}
+// ... and the 7 that do (bits 0..34: x = state ^ w0, and the low three bits of w1)
+__device__ __forceinline__ uint32_t crc_elem_chain(uint32_t x, uint32_t w1, const CrcRegs &cr) {
+  const uint32_t a = ABFT_CRC_LOOKUP(0, x) ^ ABFT_CRC_LOOKUP(1, x >> 5) ^ ABFT_CRC_LOOKUP(2, x >> 10);
+  const uint32_t b = ABFT_CRC_LOOKUP(3, x >> 15) ^ ABFT_CRC_LOOKUP(4, x >> 20) ^ ABFT_CRC_LOOKUP(5, x >> 25);
+  return a ^ b ^ ABFT_CRC_LOOKUP(6, __funnelshift_r(x, w1, 30));
+}
+
 // F^M(x) from the 5-bit chunk tables in shared memory (tab = all 21 tables); NCH chunks of x can be non-zero
 template <int M, int NCH>
 __device__ __forceinline__ uint32_t crc_map(uint32_t x, const uint32_t *tab) {
@@ -411,10 +445,12 @@ __device__ __forceinline__ uint32_t crc_element(uint32_t state, uint32_t w0, uin
 // Unrolled CRC32C row walk for regular tiles, walk_chunk's shape: all shared-memory loads, then per element the
 // gather and the state-independent two thirds of the CRC step, with the serial third (F3) chained through; the
 // products are added in element order.  For rows of 4..LEN elements (the CRC sits in the top bytes of the first
-// four column words); anything else takes the one-by-one loop.
-template <int LEN>
+// four column words); anything else takes the one-by-one loop.  WARP: every lane of the warp is here (lanes without
+// a row included), tables in registers (cr); else tables in shared memory (crc_tab).
+template <int LEN, bool WARP = false>
 __device__ __forceinline__ double walk_crc(uint32_t count, const uint32_t *s_cols, const double *s_vals, uint32_t n_cols,
-                                           const double *__restrict__ x, const uint32_t *crc_tab, bool full, bool &bad) {
+                                           const double *__restrict__ x, const uint32_t *crc_tab, bool full, bool &bad,
+                                           const CrcRegs *cr = nullptr) {
   uint32_t c[LEN];
   double v[LEN], xv[LEN];
 #pragma unroll
@@ -429,7 +465,8 @@ __device__ __forceinline__ double walk_crc(uint32_t count, const uint32_t *s_col
     xv[k] = __ldg(x + min(col, n_cols - 1u));
     uint32_t w0, w1;
     split_value(v[k], w0, w1);
-    const uint32_t next = crc_element(crc, w0, w1, col, crc_tab);
+    const uint32_t next = WARP ? (crc_elem_chain(crc ^ w0, w1, *cr) ^ crc_elem_free(w1, c[k], col, *cr))
+                               : crc_element(crc, w0, w1, col, crc_tab);
     crc = (full || (uint32_t)k < count) ? next : crc;        // slots past the row's end hold the next row's elements
   }
   // (count >= 4: the first four column words are the row's own)
@@ -520,7 +557,7 @@ template <int MODE, int FLEN = 0>
 __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_row, const uint32_t *s_rptr,
                                             const uint32_t *s_cols, const double *s_vals, const MatView &A,
                                             const double *__restrict__ x, double *__restrict__ y, const LogRef &L,
-                                            const uint32_t *s_crc, double &dot_part) {
+                                            const uint32_t *s_crc, double &dot_part, const CrcRegs &cr) {
   const uint32_t rb = t.row_begin & ~3u, cb = t.nnz_begin & ~3u, vb = t.nnz_begin & ~1u;
   const uint32_t row = t.row_begin + k;
   const uint32_t max_len = FLEN ? (uint32_t)FLEN : ((t.info >> kTileMaxLenShift) & 0xFFFu);  // uniform over the tile
@@ -543,9 +580,24 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
   const bool in_window = (MODE & 7) != ABFT_MODE_CONSTRAINTS || (rs >= t.nnz_begin && re <= t.nnz_end && rs <= re);
   // does every row of this warp fill the unrolled walk?  Lanes without a row do not veto.
   const bool full_rows = max_len <= 7 && __all_sync(0xffffffffu, !has_row || (in_window && len == need));
-  if (!has_row) return;
   double sum = 0.0;
   bool careful = true;
+  if ((MODE & 7) == ABFT_MODE_CRC32C && FLEN >= 4 && FLEN <= 7) {
+    // register tables: the whole warp walks in step (SHFL), so only if every one of its rows takes the unrolled
+    // walk; lanes without a row walk the tile's first slots and drop the result
+    if (__all_sync(0xffffffffu, !has_row || (len >= 4 && len <= need))) {
+      const uint32_t *sc0 = has_row ? s_cols + (rs - cb) : s_cols;
+      const double *sv0 = has_row ? s_vals + (rs - vb) : s_vals;
+      bool bad = false;
+      sum = walk_crc<(FLEN >= 4 && FLEN <= 7) ? FLEN : 4, true>(len, sc0, sv0, A.n_cols, x, s_crc, full_rows, bad, &cr);
+      if (!has_row) return;
+      if (bad) log_event(L, ABFT_EV_CRC_ROW, A.row_offset + row, 0);
+      y[row] = sum;
+      dot_part = __dadd_rn(dot_part, __dmul_rn(sum, xrow));
+      return;
+    }
+  }
+  if (!has_row) return;
   const uint32_t *sc = s_cols + (rs - cb);
   const double *sv = s_vals + (rs - vb);
   if ((MODE & 7) != ABFT_MODE_CRC32C && in_window) {
@@ -620,7 +672,8 @@ __device__ __forceinline__ void regular_row(const Tile &t, uint32_t k, bool has_
 // instructions per warp and tile of the ~100 that are not the walk itself (this kernel's time follows its instruction
 // count, see the notes at the refill below).
 template <int MODE, bool DYN, int FLEN = 0>
-__global__ void __launch_bounds__(SpmvCfg<DYN>::block, 4)
+// (crc32c with its tables in registers: 80 registers per thread, 3 CTAs per SM; everything else 64 and 4)
+__global__ void __launch_bounds__(SpmvCfg<DYN>::block, ((MODE & 7) == ABFT_MODE_CRC32C && FLEN) ? 3 : 4)
 spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, LogRef L, ReduceOut red,
             const int *__restrict__ active, WaitSpec wait) {
 #ifndef ABFT_HOST_EMU
@@ -644,6 +697,8 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
 
   const int tid = threadIdx.x;
   const uint32_t G = gridDim.x;
+  CrcRegs crc_regs;
+  if ((MODE & 7) == ABFT_MODE_CRC32C && FLEN) crc_regs_load(crc_regs, tid & 31);
   // Tile source.  Static: CTA b takes tiles b, b+grid, ... (the whole chip sweeps the matrix as one front; each
   // thread keeps its own dot() partial).  Dynamic (matrices with irregular tiles, whose cost per tile varies by
   // 5x): CTAs draw tiles from a counter; a tile's dot() contribution is then reduced per tile into
@@ -953,7 +1008,7 @@ spmv_kernel(MatView A, const double *__restrict__ x, double *__restrict__ y, Log
         }
       } else {
         // ---------------- regular tile: thread-per-row straight from the staged stream ----------------
-        regular_row<MODE, FLEN>(t, (uint32_t)tid, has_row, B.rptr, B.cols, B.vals, A, x, y, L, s_crc, dot_part);
+        regular_row<MODE, FLEN>(t, (uint32_t)tid, has_row, B.rptr, B.cols, B.vals, A, x, y, L, s_crc, dot_part, crc_regs);
       }
     }
     if (dynamic) {

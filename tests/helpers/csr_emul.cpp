@@ -48,6 +48,8 @@ void fill_crc_tables() {
   for (int m = 1; m <= kCrcMaps; m++)
     for (int j = 0; j < kCrcChunks; j++)
       for (uint32_t c = 0; c < 32; c++) g_crc5_tab[((m - 1) * kCrcChunks + j) * 32 + c] = crc5_entry(m, j, c);
+  for (int i = 0; i < kCrcElemChunks; i++)
+    for (uint32_t c = 0; c < 32; c++) g_crc_elem_tab[i * 32 + c] = crc_elem_entry(i, c);
 }
 
 template <int MODE, bool DYN>

@@ -31,6 +31,10 @@ static inline uint32_t __brev(uint32_t x) {
   for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);
   return r;
 }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
+  s &= 31u;
+  return s ? (lo >> s) | (hi << (32u - s)) : lo;
+}
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {
   s &= 31u;

@@ -55,6 +55,10 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
   for (int k = 0; k < 4; k++) r |= (uint32_t)((pool >> (8 * ((s >> (4 * k)) & 7u))) & 0xFFu) << (8 * k);
   return r;
 }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
+  s &= 31u;
+  return s ? (lo >> s) | (hi << (32u - s)) : lo;
+}
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline double __dadd_rn(double a, double b) { return a + b; }   // built with -ffp-contract=off

@@ -50,5 +50,21 @@ uint32_t ecc_crc32c_words_by_maps(const uint32_t *w, int n_words) {   // n_words
   for (int i = 0; i + 2 < n_words; i += 3) c = map5(3, c ^ w[i]) ^ map5(2, w[i + 1]) ^ map5(1, w[i + 2]);
   return c ^ 0xFFFFFFFFu;
 }
+// ... and with the 18 chunk tables cut from the whole 88-bit element {state ^ w0, w1, col} (crc_elem_chain / crc_elem_free
+// of spmv.cuh: the stencil kernels' check); every third word must fit 24 bits
+uint32_t ecc_crc32c_words_by_elem_chunks(const uint32_t *w, int n_words) {
+  uint32_t c = 0xFFFFFFFFu;
+  for (int i = 0; i + 2 < n_words; i += 3) {
+    const uint32_t x = c ^ w[i], w1 = w[i + 1], col = w[i + 2];
+    uint32_t r = 0;
+    for (int ch = 0; ch < kCrcElemChunks; ch++) {
+      const int p = 5 * ch;   // first bit of the chunk in the 88-bit string
+      const unsigned __int128 e = (unsigned __int128)x | ((unsigned __int128)w1 << 32) | ((unsigned __int128)col << 64);
+      r ^= crc_elem_entry(ch, (uint32_t)(e >> p) & 31u);
+    }
+    c = r;
+  }
+  return c ^ 0xFFFFFFFFu;
+}
 
 }  // extern "C"

@@ -63,10 +63,10 @@ def test_crc32c_published_vectors(E, O):
     u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
     E.ecc_crc32c_bytes.restype = C.c_uint32
     E.ecc_crc32c_bytes.argtypes = [u8p, C.c_int]
-    for f_ in (E.ecc_crc32c_words_by4, E.ecc_crc32c_words_by_maps):
+    for f_ in (E.ecc_crc32c_words_by4, E.ecc_crc32c_words_by_maps, E.ecc_crc32c_words_by_elem_chunks):
         f_.restype = C.c_uint32
         f_.argtypes = [u32p, C.c_int]
-    seen_maps = 0
+    seen_maps = seen_elem = 0
     for name, v in G["vectors"].items():
         data = bytes.fromhex(v["bytes"])
         want = int(v["crc32c"], 16)
@@ -79,7 +79,10 @@ def test_crc32c_published_vectors(E, O):
             if len(words) % 3 == 0:
                 assert E.ecc_crc32c_words_by_maps(words, len(words)) == want, name
                 seen_maps += 1
-    assert seen_maps >= 1     # the 48-byte PDU: four 96-bit elements
+                if np.all(words[2::3] < 2**24):
+                    assert E.ecc_crc32c_words_by_elem_chunks(words, len(words)) == want, name
+                    seen_elem += 1
+    assert seen_maps >= 1 and seen_elem >= 1     # the 48-byte PDU: four 96-bit elements
     # random messages: the three table forms agree with the oracle
     rng = np.random.default_rng(9)
     for n_words in (3, 6, 21, 300):
@@ -87,6 +90,9 @@ def test_crc32c_published_vectors(E, O):
         want = O.lib().orc_crc32c(words.tobytes(), 4 * n_words)
         assert E.ecc_crc32c_words_by4(words, n_words) == want == E.ecc_crc32c_words_by_maps(words, n_words)
         assert E.ecc_crc32c_bytes(words.view(np.uint8).copy(), 4 * n_words) == want
+        words[2::3] &= 0x00FFFFFF    # the 88-bit element form: columns of 24 bits
+        want = O.lib().orc_crc32c(words.tobytes(), 4 * n_words)
+        assert E.ecc_crc32c_words_by_elem_chunks(words, n_words) == want
 
 
 def test_crc32c_row_known_answer_oracle(O, pkg):

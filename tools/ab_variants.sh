@@ -2,12 +2,12 @@
 # Kernel A/B kit: build libabftcuda.so variants with compile-time knobs (here, no GPU: nvcc cross-compiles into
 # build/variants/, which travels with gpurun); tools/ab_time.py then times each on the GPU box and holds its results
 # to the first library's, bit for bit.  A variant is adopted only when it is parity-green and faster; the knob is then
-# removed.  Knobs left in the source: ABFT_SPMV_BLOCK (spmv.cuh), ABFT_CRC_MULHI (spmv.cuh).
+# removed (none is left in the source at the end of round 2).
 #   tools/ab_variants.sh build ["name:flags" ...]
 set -euo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 OUT="$ROOT/build/variants"
-VARIANTS=("base:" "blk128:-DABFT_SPMV_BLOCK=128" "blk64:-DABFT_SPMV_BLOCK=64" "crcmulhi:-DABFT_CRC_MULHI=1")
+VARIANTS=("base:")
 case "${1:-}" in
   build)
     shift

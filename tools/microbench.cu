@@ -12,7 +12,8 @@
 constexpr int kIters = 4096;
 constexpr int kChains = 8;
 
-enum Op { POPC, LOP3, IMAD, SHF, PRMT, BREV, DFMA, DADD, DMUL, IADD3, LDS32, LDS64, MIX_SECDED, FLO };
+enum Op { POPC, LOP3, IMAD, SHF, PRMT, BREV, DFMA, DADD, DMUL, IADD3, LDS32, LDS64, MIX_SECDED, FLO, IMADHI, IMADWIDE, MIX_LOP3_IMAD, MIX_LOP3_IMADHI, SHFLIDX, MIX_SHFL_LDS, MIX_SHF_SHFL };
+__constant__ unsigned g_mul[2] = {1u << 19, 1u << 9};  // opaque to ptxas: mul.hi stays a multiply
 
 template <int OP>
 __global__ void bench(unsigned long long *cycles, unsigned *sink, unsigned seed) {
@@ -30,6 +31,25 @@ __global__ void bench(unsigned long long *cycles, unsigned *sink, unsigned seed)
       if (OP == POPC) asm volatile("popc.b32 %0, %0;" : "+r"(x[c]));
       if (OP == LOP3) asm volatile("lop3.b32 %0, %0, %1, 0x5a5a5a5a, 0x96;" : "+r"(x[c]) : "r"(x[(c + 1) % kChains]));
       if (OP == IMAD) asm volatile("mad.lo.u32 %0, %0, %1, 12345;" : "+r"(x[c]) : "r"(x[(c + 1) % kChains]));
+      if (OP == IMADHI) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(g_mul[c & 1]), "r"(x[(c + 1) % kChains]));
+      if (OP == IMADWIDE) { unsigned long long w; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x[c]), "r"(g_mul[c & 1])); x[c] = (unsigned)(w >> 32) + (unsigned)w; }
+      if (OP == MIX_LOP3_IMAD) {
+        asm volatile("lop3.b32 %0, %0, %1, 0x5a5a5a5a, 0x96;" : "+r"(x[c]) : "r"(x[(c + 1) % kChains]));
+        asm volatile("mad.lo.u32 %0, %0, %1, 12345;" : "+r"(x[c]) : "r"(x[(c + 1) % kChains]));
+      }
+      if (OP == MIX_LOP3_IMADHI) {
+        asm volatile("lop3.b32 %0, %0, %1, 0x5a5a5a5a, 0x96;" : "+r"(x[c]) : "r"(x[(c + 1) % kChains]));
+        asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(g_mul[c & 1]), "r"(x[(c + 1) % kChains]));
+      }
+      if (OP == SHFLIDX) x[c] = __shfl_sync(0xffffffffu, x[(c + 1) % kChains], (int)x[c]) + c;
+      if (OP == MIX_SHFL_LDS) {
+        x[c] = __shfl_sync(0xffffffffu, x[(c + 1) % kChains], (int)x[c]) + c;
+        x[c] = ((volatile unsigned *)smem)[x[c] & 31u];
+      }
+      if (OP == MIX_SHF_SHFL) {
+        asm volatile("shf.r.wrap.b32 %0, %0, %1, 5;" : "+r"(x[c]) : "r"(x[(c + 1) % kChains]));
+        x[c] = __shfl_sync(0xffffffffu, x[(c + 1) % kChains], (int)x[c]) + c;
+      }
       if (OP == SHF) asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(x[c]) : "r"(x[(c + 1) % kChains]));
       if (OP == PRMT) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(x[c]) : "r"(x[(c + 1) % kChains]));
       if (OP == BREV) asm volatile("brev.b32 %0, %0;" : "+r"(x[c]));
@@ -103,6 +123,13 @@ int main() {
   run<LOP3>("LOP3", 1, sms);
   run<IADD3>("IADD", 1, sms);
   run<IMAD>("IMAD", 1, sms);
+  run<IMADHI>("IMAD.HI", 1, sms);
+  run<IMADWIDE>("IMAD.WIDE(+IADD)", 1, sms);
+  run<MIX_LOP3_IMAD>("LOP3+IMAD", 2, sms);
+  run<MIX_LOP3_IMADHI>("LOP3+IMAD.HI", 2, sms);
+  run<SHFLIDX>("SHFL.IDX(+IADD)", 1, sms);
+  run<MIX_SHFL_LDS>("SHFL+LDS.32", 2, sms);
+  run<MIX_SHF_SHFL>("SHF+SHFL", 2, sms);
   run<SHF>("SHF", 1, sms);
   run<PRMT>("PRMT", 1, sms);
   run<BREV>("BREV", 1, sms);
