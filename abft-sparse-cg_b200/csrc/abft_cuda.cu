@@ -13,6 +13,7 @@
 #include "encode.cuh"
 #include "spmv.cuh"
 #include "coo.cuh"
+#include "coo_stream.cuh"
 #include "vecops.cuh"
 
 using namespace abft;
@@ -1560,19 +1561,46 @@ struct abft_coo_matrix {
   uint32_t *d_perm = nullptr, *d_colptr = nullptr;
   uint32_t *d_pos = nullptr;     // grouped layout (ABFT_CUDA_COO_LAYOUT=grouped): element index -> slot; else null
   std::vector<uint32_t> h_perm;  // grouped layout: host copy, to hand the elements back in the caller's order
+  bool stream = true;            // grouped layout: the TMA-staged kernel (coo_stream.cuh); ABFT_CUDA_COO_KERNEL=direct: coo_spmv_kernel
 };
 
+// persistent grid of the streamed kernel: SMs x resident CTAs (never more CTAs than tiles)
 template <int MODE>
-static void launch_coo_spmv_mode(abft_ctx *c, const abft_coo_matrix *m, const double *vec, double *result) {
+static int coo_stream_ctas(abft_ctx *c) {
+  static int cached[64] = {0};   // per device
+  int &v = cached[c->device & 63];
+  if (v == 0) {
+    cudaFuncSetAttribute(coo_spmv_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCooDynSmem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coo_spmv_stream_kernel<MODE>, kBlock, kCooDynSmem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    v = per_sm;
+  }
+  return v * c->num_sms;
+}
+
+// returns true if dot(vec, result) was reduced along the way (slot SLOT_SPMV_DOT)
+template <int MODE>
+static bool launch_coo_spmv_mode(abft_ctx *c, const abft_coo_matrix *m, const double *vec, double *result) {
   LogRef L{c->d_log, c->h_flag};
   const int grid = std::max(1, std::min((int)((m->view.N + kBlock - 1) / kBlock), c->num_sms * 8));
-  if (m->view.pos) {
+  if (m->view.pos && m->stream) {
+    const int tiles = (int)((m->view.N + kCooTileCols - 1) / kCooTileCols);
+    ReduceOut red = make_reduce(c, SLOT_SPMV_DOT);
+    volatile double *host = red.host;
+    red.host = nullptr;   // published by the stray fix-up kernel, after it
+    red.phase = nullptr;
+    coo_spmv_stream_kernel<MODE><<<std::max(1, std::min(tiles, coo_stream_ctas<MODE>(c))), kBlock, kCooDynSmem, c->stream>>>(m->view, vec, result, L, red);
+    coo_stray_kernel<MODE, true><<<1, 32, 0, c->stream>>>(m->view, vec, result, L, red.dev, host);
+    return m->view.N > 0;
+  } else if (m->view.pos) {
     coo_spmv_kernel<MODE, true><<<grid, kBlock, 0, c->stream>>>(m->view, vec, result, L);
     coo_stray_kernel<MODE, true><<<1, 32, 0, c->stream>>>(m->view, vec, result, L);
   } else {
     coo_spmv_kernel<MODE, false><<<grid, kBlock, 0, c->stream>>>(m->view, vec, result, L);
     coo_stray_kernel<MODE, false><<<1, 32, 0, c->stream>>>(m->view, vec, result, L);
   }
+  return false;
 }
 
 extern "C" {
@@ -1602,7 +1630,8 @@ abft_coo_matrix *abft_cuda_coo_matrix_create(abft_ctx *c, const uint32_t *column
     fail(-1, "ECC modes keep the check bits in column bits 24..31: N must be <= 2^24", __FILE__, __LINE__);
     return nullptr;
   }
-  std::vector<uint32_t> colptr((size_t)N + 1, 0u), perm((size_t)std::max(nnz, 1));
+  // (colptr: kCooColptrPad entries past the end, so that the streamed kernel's 16-byte-rounded window stays inside)
+  std::vector<uint32_t> colptr((size_t)N + 1 + kCooColptrPad, (uint32_t)nnz), perm((size_t)std::max(nnz, 1));
   if (!coo_build_groups(columns, N, nnz, colptr.data(), perm.data())) {
     fail(-1, "coo_matrix_create: column index out of range", __FILE__, __LINE__);
     return nullptr;
@@ -1634,6 +1663,8 @@ abft_coo_matrix *abft_cuda_coo_matrix_create(abft_ctx *c, const uint32_t *column
   // ABFT_CUDA_COO_LAYOUT=caller asks for the caller's order (kept for the tests: both layouts against the oracle)
   const char *layout = getenv("ABFT_CUDA_COO_LAYOUT");
   const bool grouped = !(layout && !strcmp(layout, "caller")) && nnz > 0;
+  const char *kernel = getenv("ABFT_CUDA_COO_KERNEL");   // test hook: "direct" keeps coo_spmv_kernel on the grouped layout
+  m->stream = !(kernel && !strcmp(kernel, "direct"));
   std::vector<uint32_t> pos;
   if (grouped) {
     pos.resize((size_t)nnz);
@@ -1644,12 +1675,12 @@ abft_coo_matrix *abft_cuda_coo_matrix_create(abft_ctx *c, const uint32_t *column
   CKP(cudaMalloc(&m->view.elements, sizeof(uint4) * nz));
   CKP(cudaMalloc(&m->view.stray, sizeof(uint32_t) * (1 + kMaxStray)));
   CKP(cudaMalloc(&m->d_perm, sizeof(uint32_t) * nz));
-  CKP(cudaMalloc(&m->d_colptr, sizeof(uint32_t) * ((size_t)N + 1)));
+  CKP(cudaMalloc(&m->d_colptr, sizeof(uint32_t) * colptr.size()));
   CKP(cudaMalloc(&d_cols, sizeof(uint32_t) * nz));
   CKP(cudaMalloc(&d_rows, sizeof(uint32_t) * nz));
   CKP(cudaMalloc(&d_vals, sizeof(double) * nz));
   CKP(cudaMemsetAsync(m->view.stray, 0, sizeof(uint32_t), c->stream));
-  CKP(cudaMemcpyAsync(m->d_colptr, colptr.data(), sizeof(uint32_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, c->stream));
+  CKP(cudaMemcpyAsync(m->d_colptr, colptr.data(), sizeof(uint32_t) * colptr.size(), cudaMemcpyHostToDevice, c->stream));
   if (nnz > 0) {
     CKP(cudaMemcpyAsync(m->d_perm, perm.data(), sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
     CKP(cudaMemcpyAsync(d_cols, columns, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
@@ -1720,17 +1751,26 @@ int abft_cuda_coo_spmv(abft_ctx *c, abft_coo_matrix *m, const abft_vector *vec, 
   REQUIRE((uint32_t)result->N >= m->view.N && (uint32_t)vec->N >= m->view.N, "coo_spmv: vectors shorter than N");
   REQUIRE(vec->d != result->d, "coo_spmv: vec and result must not alias");
   CK(cudaSetDevice(c->device));
+  bool fused = false;
   switch (c->mode) {
-    case ABFT_MODE_NONE: launch_coo_spmv_mode<ABFT_MODE_NONE>(c, m, vec->d, result->d); break;
-    case ABFT_MODE_CONSTRAINTS: launch_coo_spmv_mode<ABFT_MODE_CONSTRAINTS>(c, m, vec->d, result->d); break;
-    case ABFT_MODE_SED: launch_coo_spmv_mode<ABFT_MODE_SED>(c, m, vec->d, result->d); break;
-    case ABFT_MODE_SEC7: launch_coo_spmv_mode<ABFT_MODE_SEC7>(c, m, vec->d, result->d); break;
-    case ABFT_MODE_SEC8: launch_coo_spmv_mode<ABFT_MODE_SEC8>(c, m, vec->d, result->d); break;
-    case ABFT_MODE_SECDED: launch_coo_spmv_mode<ABFT_MODE_SECDED>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_NONE: fused = launch_coo_spmv_mode<ABFT_MODE_NONE>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_CONSTRAINTS: fused = launch_coo_spmv_mode<ABFT_MODE_CONSTRAINTS>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_SED: fused = launch_coo_spmv_mode<ABFT_MODE_SED>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_SEC7: fused = launch_coo_spmv_mode<ABFT_MODE_SEC7>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_SEC8: fused = launch_coo_spmv_mode<ABFT_MODE_SEC8>(c, m, vec->d, result->d); break;
+    case ABFT_MODE_SECDED: fused = launch_coo_spmv_mode<ABFT_MODE_SECDED>(c, m, vec->d, result->d); break;
     default: return fail(-1, "coo_spmv: mode has no COO form", __FILE__, __LINE__);
   }
   c->launches += 2;
-  c->epoch++;  // (no fused dot here: a later abft_cuda_dot launches its own kernel)
+  c->epoch++;
+  if (fused) {
+    // dot(vec[0 .. N), result[0 .. N)) is in slot SLOT_SPMV_DOT once the stray fix-up kernel has run: a following
+    // abft_cuda_dot(vec, result) (cg.cpp:97-100) launches nothing
+    c->dot_a = vec->d;
+    c->dot_b = result->d;
+    c->dot_n = (int)m->view.N;
+    c->dot_epoch = c->epoch;
+  }
   CK(cudaGetLastError());
   return 0;
 }

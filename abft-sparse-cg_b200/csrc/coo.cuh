@@ -3,8 +3,10 @@
 //
 // STATUS: parity green on a B200 against oracle/coo_oracle.c, which is pinned against the reference
 // (tests/test_gpu_coo.py: encoded elements, result[], events, repaired elements bit for bit; CG iteration counts), in
-// both element layouts; measured on 256^3 (profiles/r2_coo_layouts.jsonl): grouped layout 0.40 ms none / 0.46 ms secded
-// = 0.81 / 0.72 of the format's own roofline (16 B per element + the two vectors), caller-order layout 0.53 / 0.60 ms.
+// both element layouts and with both kernels of the grouped layout.  Measured on 256^3, of the format's own roofline
+// (16 B per element + the two vectors; profiles/r2_coo_stream_kernel.jsonl, r2_coo_layouts.jsonl): the streamed kernel
+// of coo_stream.cuh (the default) 0.33 ms none / sed = 1.00, 0.39 ms sec7 / secded = 0.83; this file's kernels 0.41 /
+// 0.46-0.59 ms (grouped layout) and 0.53 / 0.60 ms (caller-order layout).
 //
 // The reference's loop is a scatter: for every element in index order, result[col] += value * vec[row]
 // (COO/CPUContext.cpp:104-121).  Each output entry therefore accumulates its elements in ascending element
@@ -64,6 +66,31 @@ __device__ __forceinline__ uint32_t coo_parity_bit(const uint4 &e) {
   if (CM<P>::w2) t ^= e.z & CM<P>::w2;
   if (CM<P>::w3) t ^= e.w & CM<P>::w3;
   return __popc(t) & 1u;
+}
+
+// bit 0 set iff parity P of the element is odd (the raw popcount: callers OR several and test bit 0 once)
+template <int P>
+__device__ __forceinline__ uint32_t coo_parity_pop(const uint4 &e) {
+  uint32_t t = 0;
+  if (CM<P>::w0) t ^= e.x & CM<P>::w0;
+  if (CM<P>::w1) t ^= e.y & CM<P>::w1;
+  if (CM<P>::w2) t ^= e.z & CM<P>::w2;
+  if (CM<P>::w3) t ^= e.w & CM<P>::w3;
+  return (uint32_t)__popc(t);
+}
+// bit 0 set iff the syndrome (ecc_compute_col8) is non-zero -- without assembling it
+__device__ __forceinline__ uint32_t coo_syndrome_any(const uint4 &e) {
+  return coo_parity_pop<1>(e) | coo_parity_pop<2>(e) | coo_parity_pop<3>(e) | coo_parity_pop<4>(e) | coo_parity_pop<5>(e) |
+         coo_parity_pop<6>(e) | coo_parity_pop<7>(e);
+}
+
+// bit 0 set iff one of the mode's checks trips on this element (nothing is repaired or reported here)
+template <int MODE>
+__device__ __forceinline__ uint32_t coo_suspect(const uint4 &e) {
+  if (MODE == ABFT_MODE_SED || MODE == ABFT_MODE_SEC8) return (uint32_t)__popc(e.x ^ e.y ^ e.z ^ e.w);
+  if (MODE == ABFT_MODE_SEC7) return coo_syndrome_any(e);
+  if (MODE == ABFT_MODE_SECDED) return coo_syndrome_any(e) | (uint32_t)__popc(e.x ^ e.y ^ e.z ^ e.w);
+  return 0u;
 }
 
 // ecc_compute_overall_parity (COO/ecc.h:108-112)
@@ -147,6 +174,38 @@ struct CooView {
 template <bool GROUPED>
 __device__ __forceinline__ uint32_t coo_slot_of(const CooView &A, uint32_t i) { return GROUPED ? A.pos[i] : i; }
 
+// Slow path of coo_check (a syndrome or the overall parity tripped): repair / report as the mode demands.  Out of line
+// and by value, so that the element of the fast path stays in registers (coo_word indexes it dynamically).
+struct CooFault {
+  uint4 e;
+  uint32_t ok;   // 0: the reference would have exit(1)ed at this element
+};
+template <int MODE, bool GROUPED>
+__device__ __noinline__ CooFault coo_fault(uint4 e, uint32_t ph, uint32_t k, uint4 *elements, const uint32_t *perm, DevLog *log,
+                                           volatile unsigned int *flag) {
+  const LogRef L{log, flag};
+  const uint32_t odd = (MODE == ABFT_MODE_SEC7) ? 0u : coo_overall(e);
+  const uint32_t s = coo_syndrome(e);
+  const bool repair = (MODE == ABFT_MODE_SEC7) ? (s != 0) : (odd != 0);
+  const uint32_t i = GROUPED ? perm[k] : ph;   // the element's index in the caller's numbering
+  if (repair) {
+    if (s) {
+      const uint32_t bit = coo_flipped_bit(s);
+      // a multi-bit fault can give bit >= 128, where the reference writes past its element (UB): reported, left alone
+      if (bit < 128) coo_word(e, bit / 32) ^= 1u << (bit % 32);
+      log_event(L, ABFT_EV_CORRECTED_BIT, i, bit);
+    } else {
+      e.x ^= 1u << 24;
+      log_event(L, ABFT_EV_CORRECTED_PARITY, i, 0);
+    }
+    elements[ph] = e;  // mat->elements[i] = element (COO/CPUContext.cpp:254, 311, 363)
+  } else if (MODE == ABFT_MODE_SECDED && s) {
+    log_event(L, ABFT_EV_DOUBLE_BIT, i, 0);
+    return CooFault{e, 0u};
+  }
+  return CooFault{e, 1u};
+}
+
 // Check (and repair) one element the way the mode's spmv does; logs what the reference prints.
 // Returns false if the reference would have exit(1)ed at this element.
 // `ph`: where the element is stored; `k`: its slot in perm (grouped layout: ph == k and the element's index in the
@@ -172,26 +231,16 @@ __device__ __forceinline__ bool coo_check(uint4 &e, uint32_t ph, uint32_t k, con
     return true;
   }
   if (MODE == ABFT_MODE_SEC7 || MODE == ABFT_MODE_SEC8 || MODE == ABFT_MODE_SECDED) {
-    const uint32_t odd = (MODE == ABFT_MODE_SEC7) ? 0u : coo_overall(e);
-    if (MODE == ABFT_MODE_SEC8 && !odd) return true;  // the syndrome is only looked at when the parity trips
-    const uint32_t s = coo_syndrome(e);
-    const bool repair = (MODE == ABFT_MODE_SEC7) ? (s != 0) : (odd != 0);
-    const uint32_t i = GROUPED ? ((repair || s) ? A.perm[k] : 0u) : ph;  // (grouped: only looked up when something is reported)
-    if (repair) {
-      if (s) {
-        const uint32_t bit = coo_flipped_bit(s);
-        // a multi-bit fault can give bit >= 128, where the reference writes past its element (UB): reported, left alone
-        if (bit < 128) coo_word(e, bit / 32) ^= 1u << (bit % 32);
-        log_event(L, ABFT_EV_CORRECTED_BIT, i, bit);
-      } else {
-        e.x ^= 1u << 24;
-        log_event(L, ABFT_EV_CORRECTED_PARITY, i, 0);
-      }
-      A.elements[ph] = e;  // mat->elements[i] = element (COO/CPUContext.cpp:254, 311, 363)
-    } else if (MODE == ABFT_MODE_SECDED && s) {
-      log_event(L, ABFT_EV_DOUBLE_BIT, i, 0);
-      return false;
-    }
+    // fast path: is there anything to do at all?  (SEC8 looks at the syndrome only when the overall parity trips;
+    // SEC7 has no overall parity; SECDED acts on either.)  The verdicts are OR-ed as raw popcounts, bit 0 tested once.
+    uint32_t any;
+    if (MODE == ABFT_MODE_SEC7) any = coo_syndrome_any(e);
+    else if (MODE == ABFT_MODE_SEC8) any = (uint32_t)__popc(e.x ^ e.y ^ e.z ^ e.w);
+    else any = coo_syndrome_any(e) | (uint32_t)__popc(e.x ^ e.y ^ e.z ^ e.w);
+    if (!(any & 1u)) return true;
+    const CooFault r = coo_fault<MODE, GROUPED>(e, ph, k, A.elements, A.perm, L.log, L.flag);
+    e = r.e;
+    return r.ok != 0u;
   }
   return true;
 }
@@ -205,20 +254,41 @@ __device__ __forceinline__ double coo_value(const uint4 &e) { return __hiloint2d
 
 // result[c] = sum over group c, in element order, of value * vec[row]   (separate multiply and add: no FMA,
 // like the reference build)
-// one element of group c: check / repair, then its product into `sum` (or onto the stray list, or nowhere)
+// one element of group c: check / repair (e is updated), then: does its product belong into this group's sum?  If not it
+// goes onto the stray list (its column is no longer c) or nowhere (fatal, or vec[] would be read out of bounds).
 template <int MODE, bool GROUPED>
-__device__ __forceinline__ void coo_accumulate(uint4 e, uint32_t ph, uint32_t k, uint32_t c, const CooView &A,
-                                               const double *__restrict__ vec, const LogRef &L, double &sum) {
-  if (!coo_check<MODE, GROUPED>(e, ph, k, A, L)) return;  // fatal at this element: the host stops at the first one in index order
+__device__ __forceinline__ bool coo_prepare(uint4 &e, uint32_t ph, uint32_t k, uint32_t c, const CooView &A, const LogRef &L) {
+  if (!coo_check<MODE, GROUPED>(e, ph, k, A, L)) return false;  // fatal at this element: the host stops at the first one in index order
   const uint32_t col = coo_out_index<MODE>(e);
   if (col != c) {
     // the element no longer belongs to this output entry: leave it to the fix-up kernel
     const uint32_t slot = atomicAdd(&A.stray[0], 1u);
     if (slot < kMaxStray) A.stray[1 + slot] = GROUPED ? A.perm[k] : ph;
-    return;
+    return false;
   }
-  if (e.y >= A.N) return;  // vec[] would be read out of bounds (UB in the reference): dropped, as in the oracle
-  sum = __dadd_rn(sum, __dmul_rn(coo_value(e), vec[e.y]));
+  return e.y < A.N;  // else vec[] would be read out of bounds (UB in the reference): dropped, as in the oracle
+}
+
+template <int MODE, bool GROUPED>
+__device__ __forceinline__ void coo_accumulate(uint4 e, uint32_t ph, uint32_t k, uint32_t c, const CooView &A,
+                                               const double *__restrict__ vec, const LogRef &L, double &sum) {
+  if (coo_prepare<MODE, GROUPED>(e, ph, k, c, A, L)) sum = __dadd_rn(sum, __dmul_rn(coo_value(e), vec[e.y]));
+}
+
+// grouped layout: group c = slots [kb, ke) of `elements`, in order, straight from global memory -- the next element's
+// load in flight while this one is checked (a repair only ever rewrites the element in hand, never the one already
+// fetched)
+template <int MODE>
+__device__ __forceinline__ double coo_group_from_global(const CooView &A, uint32_t kb, uint32_t ke, uint32_t c,
+                                                        const double *__restrict__ vec, const LogRef &L) {
+  double sum = 0.0;
+  uint4 nxt = kb < ke ? A.elements[kb] : make_uint4(0, 0, 0, 0);
+  for (uint32_t k = kb; k < ke; k++) {
+    const uint4 e = nxt;
+    if (k + 1 < ke) nxt = A.elements[k + 1];
+    coo_accumulate<MODE, true>(e, k, k, c, A, vec, L, sum);
+  }
+  return sum;
 }
 
 template <int MODE, bool GROUPED>
@@ -229,14 +299,7 @@ coo_spmv_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ 
     double sum = 0.0;
     const uint32_t kb = A.colptr[c], ke = A.colptr[c + 1];
     if (GROUPED) {
-      // the group is stored in place, in order: stream it, the next element's load in flight while this one is
-      // checked (a repair only ever rewrites the element in hand, never the one already fetched)
-      uint4 nxt = kb < ke ? A.elements[kb] : make_uint4(0, 0, 0, 0);
-      for (uint32_t k = kb; k < ke; k++) {
-        const uint4 e = nxt;
-        if (k + 1 < ke) nxt = A.elements[k + 1];
-        coo_accumulate<MODE, GROUPED>(e, k, k, c, A, vec, L, sum);
-      }
+      sum = coo_group_from_global<MODE>(A, kb, ke, c, vec, L);
     } else {
       for (uint32_t k = kb; k < ke; k++) {
         const uint32_t ph = A.perm[k];
@@ -250,9 +313,13 @@ coo_spmv_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ 
 // One thread.  For every output entry a stray element now points at: recompute that entry from its own
 // group (minus the members that strayed away) and the strays that target it, in ascending element index.
 // The elements were already checked / repaired by coo_spmv_kernel; nothing is logged here.
+// dot_dev / dot_host (null: no fused dot): the spmv kernel's dot(vec, result), still unpublished; every entry rewritten
+// here replaces its term, and the value then goes to the mapped word the host polls (common.cuh, grid_sum_finalize).
 template <int MODE, bool GROUPED>
-__global__ void coo_stray_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ result, LogRef L) {
+__global__ void coo_stray_kernel(CooView A, const double *__restrict__ vec, double *__restrict__ result, LogRef L,
+                                 double *dot_dev = nullptr, volatile double *dot_host = nullptr) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double dot = dot_dev ? *dot_dev : 0.0;
   // more index faults in one spmv than the list holds: the products of the ones that did not fit are lost, so
   // result[] is wrong -- said out loud (fatal), not silently (bit = 1 tells the host which list overflowed)
   if (A.stray[0] > kMaxStray) log_event(L, ABFT_EV_LOG_OVERFLOW, A.stray[0] - kMaxStray, 1u);
@@ -292,7 +359,14 @@ __global__ void coo_stray_kernel(CooView A, const double *__restrict__ vec, doub
       last = i + 1;
       first = false;
     }
+    if (dot_dev) dot = __dadd_rn(__dadd_rn(dot, -__dmul_rn(result[target], vec[target])), __dmul_rn(sum, vec[target]));
     result[target] = sum;
+  }
+  if (dot_dev) {
+    *dot_dev = dot;
+    unsigned long long bits = (unsigned long long)__double_as_longlong(dot);
+    if (bits == kSlotEmpty) bits ^= 1ull;
+    if (dot_host) *reinterpret_cast<volatile unsigned long long *>(const_cast<double *>(dot_host)) = bits;
   }
 }
 

@@ -1,6 +1,7 @@
 """COO format on the GPU (abft_cuda_coo_*) against the pinned COO oracle (oracle/coo_oracle.c).
 
-Every test runs in both element layouts (coo.cuh): the default grouped one and the caller-order one
+Every test runs in both element layouts (coo.cuh): the default grouped one -- with the streamed kernel of
+coo_stream.cuh and with coo_spmv_kernel (ABFT_CUDA_COO_KERNEL=direct) -- and the caller-order one
 (ABFT_CUDA_COO_LAYOUT=caller).  The same cases also run on the CPU against the kernels' own source through a shim of
 the CUDA built-ins (tests/test_coo_kernel_logic.py).
 
@@ -20,12 +21,17 @@ RTOL = 1e-10
 MODES = ["none", "constraints", "sed", "sec7", "sec8", "secded"]
 
 
-@pytest.fixture(params=["grouped", "caller"], autouse=True)
+@pytest.fixture(params=["grouped", "caller", "grouped_direct"], autouse=True)
 def layout(request, monkeypatch):
+    """grouped: the default (elements stored in group order, streamed through shared memory by coo_stream.cuh's kernel;
+    tiles too large to stage -- the power-law shape -- read global memory); caller: the caller's order, read through
+    `perm`; grouped_direct: the grouped layout read straight from global memory (coo_spmv_kernel)."""
+    monkeypatch.delenv("ABFT_CUDA_COO_LAYOUT", raising=False)
+    monkeypatch.delenv("ABFT_CUDA_COO_KERNEL", raising=False)
     if request.param == "caller":
         monkeypatch.setenv("ABFT_CUDA_COO_LAYOUT", "caller")
-    else:
-        monkeypatch.delenv("ABFT_CUDA_COO_LAYOUT", raising=False)
+    elif request.param == "grouped_direct":
+        monkeypatch.setenv("ABFT_CUDA_COO_KERNEL", "direct")
     return request.param
 
 
@@ -124,6 +130,35 @@ def test_constraints_violations(pkg, CO):
         assert [ctx.coo_format_event(e) for e in events] == [CO.format_event(*e) for e in ev0]
         if not fatal:
             assert np.array_equal(y.view(np.uint64), y0.view(np.uint64))
+        ctx.close()
+
+
+def test_dot_after_coo_spmv(pkg, CO, layout):
+    """abft_cuda_dot(vec, result) right after abft_cuda_coo_spmv(A, vec, result) (cg.cpp:97-100): served by the streamed
+    kernel's own reduction (no launch) -- also when the stray fix-up kernel rewrites entries of result[] afterwards (an
+    index fault in mode none moves an element to another output entry) -- and equal to the dot of what was stored."""
+    t = pkg.matgen.poisson2d(40)
+    vec = np.random.default_rng(4).standard_normal(t.N)
+    for flips in ([], [(77, 3)], [(77, 3), (901, 6), (902, 1)]):
+        ctx = pkg.CUDAContext("none")
+        A = ctx.create_coo_matrix(t.cols, t.rows, t.vals, t.N)
+        for index, bit in flips:
+            ctx.coo_flip_bit(A, index, bit)
+        v, w = ctx.create_vector(t.N), ctx.create_vector(t.N)
+        ctx.upload(v, vec)
+        ctx.coo_spmv(A, v, w)
+        n0 = ctx.launch_count()
+        got = ctx.dot(v, w)
+        if layout == "grouped":
+            assert ctx.launch_count() == n0, "the streamed kernel reduces dot(vec, result) itself"
+            assert ctx.dot(w, v) == got and ctx.launch_count() == n0
+        y = ctx.download(w)
+        exact = float(np.dot(vec, y))
+        scale = float(np.dot(np.abs(vec), np.abs(y)))
+        assert abs(got - exact) <= 1e-13 * scale, flips
+        ctx.copy_vector(w, w)                       # any write invalidates the cached value
+        again = ctx.dot(v, w)
+        assert ctx.launch_count() > n0 and abs(again - exact) <= 1e-13 * scale
         ctx.close()
 
 

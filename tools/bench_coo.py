@@ -4,12 +4,13 @@
     python tools/bench_coo.py [--mode secded] [--grid 256] [--steps 100] [--warmup 5] [--layout caller|grouped]
 
 A step = one CG iteration through the C ABI as cg.cpp drives it (abft_cuda_coo_spmv, dot, calc_xr, calc_p; two
-host-visible scalars; there is no device-resident loop for COO).  `value` = steps / device time (CUDA events on the
+host-visible scalars; there is no device-resident loop for COO; with the streamed kernel the dot is served by the spmv's
+own reduction).  `value` = steps / device time (CUDA events on the
 context's stream) with operands resident; `e2e` = a whole solve from pinned host buffers (b, x uploaded, x downloaded,
 all timed); `roofline` = the COO spmv kernel pair (group walk + stray fix-up) launched back to back, against its
 algorithmic bytes: 16 B per element (the 128-bit element, read once) + 8 B per entry of vec (read once) + 8 B per
 entry of result (written once).  `perm` / `colptr` (4 B per element / per column) are the implementation's, and are
-reported as overhead, not counted.  Written without GPU minutes left: first run is the next session's.
+reported as overhead, not counted.  Results: profiles/r2_coo_stream_kernel.jsonl.
 """
 import argparse
 import json
@@ -32,7 +33,12 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--layout", default="grouped", choices=["caller", "grouped"])
+    ap.add_argument("--kernel", default="stream", choices=["stream", "direct"],
+                    help="grouped layout: the TMA-staged kernel (coo_stream.cuh) or coo_spmv_kernel")
     a = ap.parse_args()
+    os.environ.pop("ABFT_CUDA_COO_KERNEL", None)
+    if a.kernel == "direct":
+        os.environ["ABFT_CUDA_COO_KERNEL"] = "direct"
     if a.layout == "caller":
         os.environ["ABFT_CUDA_COO_LAYOUT"] = "caller"
     else:
@@ -118,12 +124,12 @@ def main():
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"poisson3d_{n} as COO (cg-coo: 128-bit elements; N={N}, nnz={nnz}), mode {a.mode}, -c 0 -i K",
-                       "layout": a.layout, "l2": f"inputs larger than L2 (element stream {16 * nnz / 1e6:.0f} MB per iteration)",
+                       "layout": a.layout, "kernel": a.kernel if a.layout == "grouped" else "direct", "l2": f"inputs larger than L2 (element stream {16 * nnz / 1e6:.0f} MB per iteration)",
                        "abi": "C ABI of include/abft_cuda.h via ctypes; host-driven loop (coo_spmv, dot, calc_xr, calc_p)"},
             "e2e": {"value": a.steps / e2e_s, "unit": "it/s", "h2d_bytes_per_step": 16.0 * N / a.steps,
                     "d2h_bytes_per_step": 8.0 * N / a.steps, "what": "b,x uploaded from pinned host buffers + K iterations + x downloaded"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": f"coo_spmv_kernel<{a.mode}> (+ stray fix-up)", "achieved": b_spmv / ms_spmv / 1e6,
+            "roofline": {"bound": "hbm", "kernel": ("coo_spmv_stream_kernel" if a.layout == "grouped" and a.kernel == "stream" else "coo_spmv_kernel") + f"<{a.mode}> (+ stray fix-up)", "achieved": b_spmv / ms_spmv / 1e6,
                          "peak": peak, "unit": "GB/s", "frac": b_spmv / ms_spmv / 1e6 / peak, "traffic": None,
                          "peak_source": peak_src, "bytes_per_launch": b_spmv, "ms_per_launch": ms_spmv,
                          "implementation_overhead_bytes": 4 * nnz * (a.layout == "caller") + 4 * N},
