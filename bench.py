@@ -28,6 +28,8 @@ What the JSON line holds:
                          same keys (relative difference of rr <= 1e-10 is the north_star's bar).
   workloads              BASELINE configs[3] (512^2 -b 64, sec8) and configs[4] (power-law, sec7 / constraints) at
                          their named sizes on the same N GPUs, time-boxed.
+  formats                (N = 1) the reference's second format, COO (cg-coo), on the primary matrix in the primary mode:
+                         it/s through the C ABI, spmv kernel pair against the format's own roofline.
 """
 import argparse
 import ctypes
@@ -467,6 +469,64 @@ def brief(case, steps, peak):
     return out
 
 
+def coo_brief(pkg, t, mode, steps, peak):
+    """The reference's second format (cg-coo) on the same matrix: CG through the C ABI the way cg.cpp drives
+    it (abft_cuda_coo_spmv, dot -- served by the spmv's own reduction --, calc_xr, calc_p) and the spmv kernel pair back
+    to back, against the format's own algorithmic bytes (16 B per element + the two vectors); tools/bench_coo.py is
+    the long form."""
+    import torch
+    N, nnz = t.N, int(t.cols.shape[0])
+    ctx = pkg.CUDAContext(mode, 0)
+    t0 = time.time()
+    A = ctx.create_coo_matrix(t.cols, t.rows, t.vals, N)
+    ctx.sync()
+    t_create = time.time() - t0
+    stream = torch.cuda.ExternalStream(ctx.L.abft_cuda_ctx_stream(ctx.ctx))
+    vb, x, r, p, w = (ctx.create_vector(N) for _ in range(5))
+    ctx.upload(vb, rhs(N))
+    ctx.upload(x, np.zeros(N))
+    ctx.copy_vector(r, vb)
+    ctx.copy_vector(p, r)
+    rr = ctx.dot(r, r)
+
+    def iterations(k, rr):
+        for _ in range(k):
+            ctx.coo_spmv(A, p, w)
+            pw = ctx.dot(p, w)
+            rr_new = ctx.calc_xr(x, r, p, w, rr / pw)
+            ctx.calc_p(p, r, rr_new / rr)
+            rr = rr_new
+        return rr
+
+    rr = iterations(5, rr)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    n0 = ctx.launch_count()
+    e0.record(stream)
+    rr = iterations(steps, rr)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    launches = ctx.launch_count() - n0
+    ms_step = e0.elapsed_time(e1) / steps
+    for _ in range(5):
+        ctx.coo_spmv(A, p, w)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(30):
+        ctx.coo_spmv(A, p, w)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_spmv = e0.elapsed_time(e1) / 30
+    events, fatal = ctx.poll_events()
+    ctx.close()
+    b_spmv = 16 * nnz + 16 * N
+    b_iter = b_spmv + 72 * N
+    return {"workload": f"the same matrix as COO (128-bit elements, N={N}, nnz={nnz}), mode {mode}", "it_s": 1e3 / ms_step,
+            "ms_per_step": ms_step, "iter_frac": b_iter / ms_step / 1e6 / peak, "spmv_ms": ms_spmv,
+            "spmv_frac": b_spmv / ms_spmv / 1e6 / peak, "bytes_per_spmv": b_spmv, "gpu_launches": int(launches),
+            "rr_after": {"iterations": 5 + steps, "rr": rr}, "faults": len(events), "setup": {"create_matrix_s": t_create}}
+
+
 def main():
     global _REAL_STDOUT
     t_start = time.time()
@@ -663,6 +723,18 @@ def main():
             except Exception as e:      # an optional section must not take the headline down with it
                 wl[f"{name}_{mode}"] = {"error": repr(e)[:300]}
         line["workloads"] = wl
+
+    # ---- the COO format on the primary matrix, N = 1 ----
+    if world == 1 and args.all_modes and args.workload == "poisson3d":
+        if over_budget():
+            line["formats"] = {"coo_" + args.mode: {"skipped": "time budget (--budget-s)"}}
+        elif args.mode in ("crc32c", "secdedv"):
+            line["formats"] = {"coo_" + args.mode: {"skipped": "CSR-only mode"}}
+        else:
+            try:
+                line["formats"] = {"coo_" + args.mode: coo_brief(pkg, t_primary, args.mode, min(K, 100), peak)}
+            except Exception as e:      # an optional section must not take the headline down with it
+                line["formats"] = {"coo_" + args.mode: {"error": repr(e)[:300]}}
 
     # ---- CPU baseline: the reference's CPU target on this box's host cores, bounded sample ----
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
