@@ -26,7 +26,8 @@ SYMBOLS = [
     "abft_cuda_matrix_poke_col", "abft_cuda_matrix_poke_value",
     "abft_cuda_vector_create", "abft_cuda_vector_wrap", "abft_cuda_vector_view", "abft_cuda_vector_destroy",
     "abft_cuda_vector_len", "abft_cuda_vector_flip_bit", "abft_cuda_vector_dev_ptr", "abft_cuda_vector_map", "abft_cuda_vector_unmap",
-    "abft_cuda_vector_copy",
+    "abft_cuda_vector_copy", "abft_cuda_vector_download_async", "abft_cuda_vector_upload_async", "abft_cuda_host_alloc",
+    "abft_cuda_host_free",
     "abft_cuda_spmv", "abft_cuda_dot", "abft_cuda_calc_xr", "abft_cuda_calc_p",
     "abft_cuda_dot_async", "abft_cuda_calc_xr_async", "abft_cuda_scalar_dev_ptr", "abft_cuda_scalar_host",
     "abft_cuda_flip_bit", "abft_cuda_poll_events", "abft_cuda_events_pending",
@@ -106,6 +107,10 @@ def load():
     sig("abft_cuda_vector_map", f64p, vp, vp)
     sig("abft_cuda_vector_unmap", i32, vp, vp, vp)
     sig("abft_cuda_vector_copy", i32, vp, vp, vp)
+    sig("abft_cuda_vector_download_async", i32, vp, vp, vp)
+    sig("abft_cuda_vector_upload_async", i32, vp, vp, vp)
+    sig("abft_cuda_host_alloc", vp, C.c_size_t)
+    sig("abft_cuda_host_free", None, vp)
     sig("abft_cuda_spmv", i32, vp, vp, vp, vp)
     sig("abft_cuda_dot", i32, vp, vp, vp, f64p)
     sig("abft_cuda_calc_xr", i32, vp, vp, vp, vp, vp, f64, f64p)

@@ -764,6 +764,43 @@ int abft_cuda_vector_unmap(abft_ctx *c, abft_vector *v, const double *h) {
   return 0;
 }
 
+int abft_cuda_vector_download_async(abft_ctx *c, abft_vector *v, double *host_dst) {
+  REQUIRE(c && v && (host_dst || v->N == 0), "null argument");
+  CK(cudaSetDevice(c->device));
+  if (c->vsed && v->N) {
+    vec_check_kernel<<<vec_grid(c, v->N), kBlock, 0, c->stream>>>(v->d, v->N, LogRef{c->d_log, c->h_flag});
+    c->launches++;
+  }
+  if (v->N) CK(cudaMemcpyAsync(host_dst, v->d, sizeof(double) * (size_t)v->N, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+int abft_cuda_vector_upload_async(abft_ctx *c, abft_vector *v, const double *host_src) {
+  REQUIRE(c && v && (host_src || v->N == 0), "null argument");
+  CK(cudaSetDevice(c->device));
+  if (v->N) CK(cudaMemcpyAsync(v->d, host_src, sizeof(double) * (size_t)v->N, cudaMemcpyHostToDevice, c->stream));
+  if (c->vsed && v->N) {
+    vec_encode_kernel<<<vec_grid(c, v->N), kBlock, 0, c->stream>>>(v->d, v->N);
+    c->launches++;
+  }
+  c->epoch++;
+  return 0;
+}
+
+void *abft_cuda_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    fail(-1, "host_alloc: cudaHostAlloc failed", __FILE__, __LINE__);
+    return nullptr;
+  }
+  return p;
+}
+
+void abft_cuda_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 int abft_cuda_vector_copy(abft_ctx *c, abft_vector *dst, const abft_vector *src) {
   REQUIRE(c && dst && src, "null argument");
   REQUIRE(src->N >= dst->N, "copy_vector: source shorter than destination");

@@ -154,7 +154,7 @@ class CUDAContext : public CGContext {
       }
     }
     for (int d = 0; d < G; d++) abft_cuda_vector_destroy(ctx[d], vec->full[d]);
-    free(vec->host);
+    abft_cuda_host_free(vec->host);
     delete vec;
   }
   virtual double *map_vector(cg_vector *v) {
@@ -165,12 +165,14 @@ class CUDAContext : public CGContext {
       return h;
     }
     prepare(v);
-    if (!v->host) v->host = (double *)malloc(sizeof(double) * (size_t)(v->N > 0 ? v->N : 1));
-    for (int d = 0; d < G; d++) {
-      double *h = abft_cuda_vector_map(ctx[d], v->loc[d]);
-      if (!h) die("map_vector");
-      memcpy(v->host + cut[d], h, sizeof(double) * (size_t)(cut[d + 1] - cut[d]));
-    }
+    // one pinned host image of the vector (usable with every GPU); each GPU copies its slice straight into it, all
+    // copies in flight before the first wait
+    if (!v->host) v->host = (double *)abft_cuda_host_alloc(sizeof(double) * (size_t)(v->N > 0 ? v->N : 1));
+    if (!v->host) die("map_vector (host buffer)");
+    for (int d = 0; d < G; d++)
+      if (abft_cuda_vector_download_async(ctx[d], v->loc[d], v->host + cut[d])) die("map_vector");
+    for (int d = 0; d < G; d++)
+      if (abft_cuda_ctx_sync(ctx[d])) die("map_vector (sync)");
     report_faults();
     return v->host;
   }
@@ -181,7 +183,9 @@ class CUDAContext : public CGContext {
     }
     prepare(v);
     for (int d = 0; d < G; d++)
-      if (abft_cuda_vector_unmap(ctx[d], v->loc[d], h + cut[d])) die("unmap_vector");
+      if (abft_cuda_vector_upload_async(ctx[d], v->loc[d], h + cut[d])) die("unmap_vector");
+    for (int d = 0; d < G; d++)   // (the caller may reuse h as soon as this returns)
+      if (abft_cuda_ctx_sync(ctx[d])) die("unmap_vector (sync)");
     v->dirty = true;
   }
   virtual void copy_vector(cg_vector *dst, const cg_vector *src) {

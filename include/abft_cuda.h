@@ -23,6 +23,7 @@
 #ifndef ABFT_CUDA_H
 #define ABFT_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -164,6 +165,15 @@ double *abft_cuda_vector_map(abft_ctx *ctx, abft_vector *v);
  * returned, or any host buffer of N doubles). */
 int abft_cuda_vector_unmap(abft_ctx *ctx, abft_vector *v, const double *h);
 int abft_cuda_vector_copy(abft_ctx *ctx, abft_vector *dst, const abft_vector *src);
+/* The same two transfers for a caller that owns the host buffer -- the plugin with several GPUs under one host thread
+ * keeps ONE host image of a vector and moves each GPU's slice of it: asynchronous device->host / host->device copy
+ * of all N entries on the context's stream (mode secdedv checks / encodes like map / unmap);
+ * abft_cuda_ctx_sync() completes it.  abft_cuda_host_alloc: pinned host memory usable with every device of the
+ * process (so that the slices move concurrently and without a staging copy); NULL on failure. */
+int abft_cuda_vector_download_async(abft_ctx *ctx, abft_vector *v, double *host_dst);
+int abft_cuda_vector_upload_async(abft_ctx *ctx, abft_vector *v, const double *host_src);
+void *abft_cuda_host_alloc(size_t bytes);
+void abft_cuda_host_free(void *p);
 
 /* ---- the hot path (cg.cpp:97-112) ---- */
 /* spmv: result = A * vec, ABFT check/correct of the context's mode fused into

@@ -12,7 +12,7 @@ typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorNotReady = 600, cudaErrorNotSupported = 801, cudaErrorPeerAccessAlreadyEnabled = 704 };
 typedef struct emu_stream_t *cudaStream_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaHostAllocMapped = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaHostAllocMapped = 2, cudaHostAllocPortable = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 struct cudaDeviceProp { int multiProcessorCount; };
 struct cudaIpcMemHandle_t { char reserved[64]; };

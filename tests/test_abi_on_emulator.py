@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
 
 # the default run keeps what takes seconds; ABFT_SLOW_TESTS=1 adds the device-resident loop, CONSTRAINTS row-pointer faults
 # and the serial event order (about ten minutes: every CTA barrier is a 256-thread rendezvous)
-SUBSET = "empty_matrix or ecc_modes_reject or fused_dot or unaligned or vector_kernels"
+SUBSET = "empty_matrix or ecc_modes_reject or fused_dot or unaligned or vector_kernels or vector_transfers"
 if os.environ.get("ABFT_SLOW_TESTS") == "1":
     SUBSET += " or device_resident_loop or constraints_row_pointer_faults or multiple_faults_are_reported"
 

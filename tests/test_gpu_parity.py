@@ -272,6 +272,38 @@ def test_fused_dot_equals_standalone_dot(pkg, O):
 
 
 # ---------------------------------------------------------------- vector kernels
+def test_vector_transfers_into_caller_buffers(pkg):
+    """abft_cuda_vector_download_async / upload_async with a buffer from abft_cuda_host_alloc (what the plugin's
+    map_vector / unmap_vector do with several GPUs under one host thread: one host image, one slice per GPU) move
+    the same bytes as map / unmap, and an upload invalidates a cached fused dot like any other write."""
+    import ctypes as C
+    N = 70001
+    ctx = pkg.CUDAContext("secded")
+    L = ctx.L
+    L.abft_cuda_host_alloc.restype = C.c_void_p
+    buf = L.abft_cuda_host_alloc(C.c_size_t(8 * 2 * N))
+    assert buf
+    host = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(2 * N,))
+    data = np.random.default_rng(3).standard_normal(N)
+    host[:N] = data
+    host[N:] = 0.0
+    a, b = ctx.create_vector(N), ctx.create_vector(N)
+    assert L.abft_cuda_vector_upload_async(ctx.ctx, a.handle, C.c_void_p(buf)) == 0
+    ctx.copy_vector(b, a)
+    assert L.abft_cuda_vector_download_async(ctx.ctx, b.handle, C.c_void_p(buf + 8 * N)) == 0
+    ctx.sync()
+    assert np.array_equal(host[N:].view(np.uint64), data.view(np.uint64))
+    assert np.array_equal(ctx.download(a).view(np.uint64), data.view(np.uint64))
+    d0 = ctx.dot(a, b)
+    host[:N] = 2.0 * data
+    assert L.abft_cuda_vector_upload_async(ctx.ctx, a.handle, C.c_void_p(buf)) == 0
+    ctx.sync()
+    d1 = ctx.dot(a, b)
+    assert abs(d1 - 2.0 * d0) <= 1e-12 * abs(d0)
+    L.abft_cuda_host_free(C.c_void_p(buf))
+    ctx.close()
+
+
 @pytest.mark.parametrize("N", [1, 2, 7, 1000, 65537, 1 << 20])
 def test_vector_kernels(pkg, O, N):
     L = O.lib()
