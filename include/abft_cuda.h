@@ -302,7 +302,8 @@ int abft_cuda_matrix_tiles(const abft_matrix *mat);
 /* ---------------------------------------------------------------------------
  * COO format -- the reference's second executable, cg-coo (COO/CPUContext.h:17-22 struct cg_matrix
  * {N, nnz, coo_element*}; COO/CPUContext.cpp).  Vectors, dot, calc_xr, calc_p and the fault log are the
- * ones above.  STATUS: parity green on a B200 against the pinned COO oracle (tests/test_gpu_coo.py); not yet tuned.
+ * ones above.  STATUS: parity green on a B200 against the pinned COO oracle (tests/test_gpu_coo.py); the default kernel
+ * streams the elements through shared memory (csrc/coo_stream.cuh): 0.83 (secded) .. 1.0 (none) of the format's roofline.
  * ------------------------------------------------------------------------- */
 typedef struct abft_coo_matrix abft_coo_matrix;
 
@@ -317,7 +318,8 @@ int abft_cuda_coo_matrix_nnz(const abft_coo_matrix *mat);
 int abft_cuda_coo_matrix_read(abft_ctx *ctx, const abft_coo_matrix *mat, void *elements_out);
 /* CPUContext*::spmv (COO/CPUContext.cpp:104-121, 142-194, 201-228, 235-267, 275-318, 326-379):
  * result[col] += value * vec[row] in element order per output entry; faults go to the context's log
- * (abft_cuda_poll_events), formatted with abft_cuda_coo_format_event. */
+ * (abft_cuda_poll_events), formatted with abft_cuda_coo_format_event.  Like abft_cuda_spmv it leaves dot(vec, result)
+ * behind, so the abft_cuda_dot(vec, result) that cg.cpp:100 issues next costs no pass. */
 int abft_cuda_coo_spmv(abft_ctx *ctx, abft_coo_matrix *mat, const abft_vector *vec, abft_vector *result);
 /* the RMW of CPUContext::inject_bitflip (COO/CPUContext.cpp:138): bit 0..127 of element `index`
  * (0..31 col, 32..63 row, 64..127 value); the plugin draws index and bits with rand() like :125,136 */
