@@ -52,3 +52,9 @@ def test_gpu_coo_subset_on_the_emulated_library(emu_lib):
     out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_coo.py", "-m", "gpu", "-x", "-q", "-k", sel],
                          cwd=ROOT, capture_output=True, text=True, timeout=1500, env={**os.environ, "ABFT_CUDA_LIB": emu_lib})
     assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-1500:]
+    # ... and the COO differential fuzz of tests/test_gpu_fuzz.py, a few trials per mode (ABFT_SLOW_TESTS=1: 300)
+    trials = "300" if os.environ.get("ABFT_SLOW_TESTS") == "1" else "15"
+    out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_fuzz.py", "-m", "gpu", "-x", "-q", "-k", "coo_oracle"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=1500,
+                         env={**os.environ, "ABFT_CUDA_LIB": emu_lib, "ABFT_FUZZ_TRIALS": trials})
+    assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-1500:]
