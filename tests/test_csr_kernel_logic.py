@@ -523,3 +523,34 @@ def test_stencil_matrices_get_the_fixed_length_instantiation(EMU, pkg):
         em = EmuMatrix(EMU, pkg, "secded", shapes(pkg.matgen)[name]())
         assert EMU.emu_flen(em.h) == want, name
         em.close()
+
+
+def test_crc32c_register_tables_with_columns_up_to_2_24(EMU, pkg, O):
+    """The stencil instantiation's CRC check cuts 18 five-bit chunks from the whole 88-bit element; the last ones hold
+    column bits 16..23, which the small test matrices never set.  The last 160 rows of a 2^24-column matrix (one rank's
+    block of a row partition), 7 elements each with columns all over [0, 2^24): clean, and with every bit of one
+    element's column field flipped in turn, against the oracle."""
+    N = 1 << 24
+    r0 = N - 160
+    rng = np.random.default_rng(24)
+    rows = np.repeat(np.arange(r0, N), 7)
+    cols = np.concatenate([np.sort(rng.choice(N, 7, replace=False)) for _ in range(160)])
+    cols[-1] = N - 1                                                  # every column bit set
+    t = pkg.matgen.Triplets(cols, rows, rng.standard_normal(rows.shape[0]), N)
+    vec = rng.standard_normal(N)
+    em = EmuMatrix(EMU, pkg, "crc32c", t, rows=(r0, N))
+    assert EMU.emu_flen(em.h) == 7 and int((em.cols & 0x00FFFFFF).max()) == N - 1
+    om = O.OracleMatrix("crc32c", t.cols, t.rows, t.vals, N)
+    assert np.array_equal(em.cols, om.cols)                           # same stored CRC bytes
+    y, fatal, events, _ = em.spmv(vec)
+    y0, fatal0, ev0 = om.spmv(vec)
+    assert not fatal and events == [] == ev0
+    assert np.array_equal(y.view(np.uint64), y0[r0:].view(np.uint64))
+    index = 7 * 77 + 3
+    for bit in range(64, 88):
+        em.flip(index, bit); om.flip(index, bit)
+        y, fatal, events, _ = em.spmv(vec)
+        y0, fatal0, ev0 = om.spmv(vec)
+        assert (fatal, events) == (fatal0, ev0) and fatal, bit        # [CRC32C] error detected in row r0 + 77
+        em.flip(index, bit); om.flip(index, bit)
+    em.close()
